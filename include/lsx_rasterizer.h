@@ -1,0 +1,204 @@
+/*
+ * lsx_rasterizer.h — C ABI of the B200-native LangSurf rasterizer + KNN initialisation library
+ * (liblsx_b200.so).  Plain C: raw device pointers, sizes, an opaque stream handle, int status.
+ * No torch / C++ types cross this boundary, no exception ever leaves the library.
+ *
+ * Each entry point replaces one function of the reference's native layer
+ * (paths relative to field_construction/submodules/ in the reference tree):
+ *
+ *   lsx_rasterize_forward    <- CudaRasterizer::Rasterizer::forward   diff-langsurf-rasterizer/cuda_rasterizer/rasterizer.h:34-66
+ *                               as called by RasterizeGaussiansCUDA     diff-langsurf-rasterizer/rasterize_points.cu:35-143
+ *   lsx_rasterize_backward   <- CudaRasterizer::Rasterizer::backward  diff-langsurf-rasterizer/cuda_rasterizer/rasterizer.h:68-107
+ *                               as called by RasterizeGaussiansBackwardCUDA  rasterize_points.cu:145-259
+ *   lsx_mark_visible         <- CudaRasterizer::Rasterizer::markVisible  rasterizer.h:27-32 / rasterize_points.cu:261-280
+ *   lsx_knn_mean_dist2       <- SimpleKNN::knn / distCUDA2             simple-knn/simple_knn.h:16, simple-knn/spatial.cu:15-25
+ *   lsx_alloc_fn             <- std::function<char*(size_t)> from resizeFunctional  rasterize_points.cu:27-33
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the name ends in _host;
+ *     NULL means "absent" exactly like the reference's empty tensors (forward.cu:205,241).
+ *   - all float tensors are contiguous fp32, integer tensors int32, row-major as in the reference
+ *     (means3D (P,3), shs (P,M,3), opacities (P,1), scales (P,3), rotations (P,4) un-normalised,
+ *     cov3D_precomp (P,6), all_map (P,5), viewmatrix/projmatrix 16 floats in the reference's
+ *     transposed ("row-vector") memory order, images planar CHW).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.  The library holds no
+ *     device-global state between calls: several forwards may be outstanding before their backwards.
+ *   - return value 0 = success, negative = error; lsx_last_error() returns a thread-local message.
+ *   - OUTPUT INITIALISATION: callers pass UNINITIALISED output / gradient buffers.  The library writes
+ *     every element (zero where the reference's torch::full / torch::zeros would have left zero).
+ */
+#ifndef LSX_RASTERIZER_H_INCLUDED
+#define LSX_RASTERIZER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LSX_API __attribute__((visibility("default")))
+#else
+#define LSX_API
+#endif
+
+#define LSX_ABI_VERSION 1
+#define LSX_MAX_BLEND_CHANNELS 40 /* 3 + F + Fi + 5 must not exceed this */
+
+/* scratch allocation callback: must return a device pointer to at least `bytes` bytes, aligned to
+ * >= 256 B, that stays valid until the matching backward call has been enqueued. */
+typedef char* (*lsx_alloc_fn)(void* user, size_t bytes);
+
+typedef struct lsx_forward_args {
+    /* sizes / scalars (GaussianRasterizationSettings, diff_LangSurf_rasterization/__init__.py:189-203) */
+    int32_t P;             /* number of Gaussians                               */
+    int32_t D;             /* active SH degree (0..3)                           */
+    int32_t M;             /* SH coefficients per colour stored in `shs` (0 if shs absent) */
+    int32_t W, H;          /* image width / height                              */
+    int32_t F;             /* language feature width (run-time; reference: compile-time 3)  */
+    int32_t Fi;            /* instance feature width (reference: 3)            */
+    float tanfovx, tanfovy;
+    float scale_modifier;
+    int32_t prefiltered;
+    int32_t render_geo;
+    int32_t debug;         /* !=0: synchronise + check after every stage (auxiliary.h:166-173) */
+    int32_t include_feature;
+    /* inputs */
+    const float* background;                 /* 3  */
+    const float* means3D;                    /* P*3 */
+    const float* shs;                        /* P*M*3 or NULL */
+    const float* colors_precomp;             /* P*3 or NULL */
+    const float* language_feature;           /* P*F  (include_feature) */
+    const float* language_feature_instance;  /* P*Fi (include_feature) */
+    const float* opacities;                  /* P */
+    const float* scales;                     /* P*3 or NULL */
+    const float* rotations;                  /* P*4 or NULL */
+    const float* cov3D_precomp;              /* P*6 or NULL */
+    const float* all_map;                    /* P*5 (render_geo) */
+    const float* viewmatrix;                 /* 16 */
+    const float* projmatrix;                 /* 16 */
+    const float* campos;                     /* 3  */
+    /* outputs (uninitialised on entry, fully written on return) */
+    float* out_color;                        /* 3*H*W  */
+    float* out_language_feature;             /* F*H*W  if include_feature else untouched */
+    float* out_language_feature_instance;    /* Fi*H*W if include_feature else untouched */
+    int32_t* radii;                          /* P */
+    int32_t* out_observe;                    /* P */
+    float* out_all_map;                      /* 5*H*W (zeros when !render_geo) */
+    float* out_plane_depth;                  /* H*W   (zeros when !render_geo) */
+    /* scratch (private layout; contents are consumed by lsx_rasterize_backward) */
+    lsx_alloc_fn geom_alloc;    void* geom_user;
+    lsx_alloc_fn binning_alloc; void* binning_user;
+    lsx_alloc_fn image_alloc;   void* image_user;
+    void* stream;
+} lsx_forward_args;
+
+/* Returns 0 and stores the number of (Gaussian,tile) duplicates in *num_rendered.
+ * Performs exactly one host<-device read (num_rendered), like rasterizer_impl.cu:291. */
+LSX_API int lsx_rasterize_forward(const lsx_forward_args* args, int32_t* num_rendered);
+
+typedef struct lsx_backward_args {
+    int32_t P, D, M, W, H, F, Fi;
+    int32_t R;                 /* num_rendered returned by the forward call */
+    float tanfovx, tanfovy, scale_modifier;
+    int32_t render_geo, debug, include_feature;
+    /* forward inputs again */
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* language_feature;
+    const float* language_feature_instance;
+    const float* all_map;
+    const float* scales;
+    const float* rotations;
+    const float* cov3D_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    const int32_t* radii;
+    /* saved forward results */
+    const float* out_all_map;          /* "all_map_pixels", 5*H*W */
+    const char* geom_buffer;
+    const char* binning_buffer;
+    const char* image_buffer;
+    /* upstream gradients, planar like the forward outputs */
+    const float* dL_dout_color;                      /* 3*H*W */
+    const float* dL_dout_language_feature;           /* F*H*W  (include_feature) */
+    const float* dL_dout_language_feature_instance;  /* Fi*H*W (include_feature) */
+    const float* dL_dout_all_map;                    /* 5*H*W  (render_geo) */
+    const float* dL_dout_plane_depth;                /* H*W    (render_geo) */
+    /* gradient outputs (uninitialised on entry, fully written on return) */
+    float* dL_dmeans2D;      /* P*3, .z = 0 */
+    float* dL_dmeans2D_abs;  /* P*3, .z = 0 */
+    float* dL_dconic;        /* P*4 as {x,y,0,w} (backward.cu:669-671) */
+    float* dL_dopacity;      /* P */
+    float* dL_dcolors;       /* P*3 */
+    float* dL_dlanguage_feature;           /* P*F  if include_feature else untouched */
+    float* dL_dlanguage_feature_instance;  /* P*Fi if include_feature else untouched */
+    float* dL_dmeans3D;      /* P*3 */
+    float* dL_dcov3D;        /* P*6 */
+    float* dL_dsh;           /* P*M*3 (may be NULL when M == 0) */
+    float* dL_dscales;       /* P*3 */
+    float* dL_drotations;    /* P*4 */
+    float* dL_dall_map;      /* P*5 */
+    void* stream;
+} lsx_backward_args;
+
+LSX_API int lsx_rasterize_backward(const lsx_backward_args* args);
+
+/* present[i] = (view-space z of means3D[i]) > 0.2   (auxiliary.h:139-164, rasterizer_impl.cu:54-66) */
+LSX_API int lsx_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* out[i] = mean of the 3 smallest squared distances from points[i] to the other points
+ * (simple_knn.cu:147-183).  Scratch comes from `alloc` (one call).  */
+LSX_API int lsx_knn_mean_dist2(int32_t P, const float* points, float* out, lsx_alloc_fn alloc, void* alloc_user,
+                       void* stream);
+
+/* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
+
+/* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the
+ * bit-exact intermediates the way SURVEY.md Appendix B reads the reference's. */
+typedef struct lsx_scratch_layout {
+    /* geometry buffer, P rows */
+    size_t depths;         /* f32[P]   view-space z                              */
+    size_t clamped;        /* u8[P]    bit c set if SH colour channel c was clamped at 0 */
+    size_t means2D;        /* f32[2P]  pixel-space centre                        */
+    size_t cov3D;          /* f32[6P]                                            */
+    size_t conic_opacity;  /* f32[4P]                                            */
+    size_t rgb;            /* f32[3P]                                            */
+    size_t tiles_touched;  /* u32[P]                                             */
+    size_t records;        /* f32[P*record_stride] packed per-Gaussian blend record */
+    int32_t record_stride; /* floats */
+    size_t geom_bytes;
+    /* image buffer */
+    size_t final_T;        /* f32[W*H] */
+    size_t n_contrib;      /* u32[W*H] */
+    size_t ranges;         /* u32[2*tiles] (start,end) */
+    size_t image_bytes;
+    /* binning buffer, R rows */
+    size_t point_list;     /* u32[R] sorted Gaussian indices */
+    size_t binning_bytes;
+} lsx_scratch_layout;
+
+LSX_API int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,
+                             lsx_scratch_layout* out);
+
+/* Materialise the sorted 64-bit keys (tile << 32 | depth bits) the reference keeps in
+ * BinningState::point_list_keys (rasterizer_impl.cu:102-106), from this library's scratch. */
+LSX_API int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,
+                          const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
+                          uint64_t* keys_out, void* stream);
+
+/* number of kernels launched by this library since process start (bench.py "gpu_launches") */
+LSX_API uint64_t lsx_kernel_launch_count(void);
+
+LSX_API const char* lsx_last_error(void);
+LSX_API int lsx_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSX_RASTERIZER_H_INCLUDED */

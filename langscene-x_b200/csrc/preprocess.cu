@@ -1,0 +1,549 @@
+// preprocess.cu — per-Gaussian stage of the rasterizer (forward K1, backward K8+K9 fused, markVisible).
+//
+// Reference behaviour restated here (paths under field_construction/submodules/diff-langsurf-rasterizer/):
+//   forward : cuda_rasterizer/forward.cu:21-268  (SH->RGB, cov3D, EWA cov2D, conic, radius, tile rect)
+//             cuda_rasterizer/auxiliary.h:41-56,139-164 (ndc2Pix in double, getRect, near cull z<=0.2)
+//   backward: cuda_rasterizer/backward.cu:20-139 (SH), :144-274 (cov2D), :278-341 (cov3D), :346-396
+//
+// B200 design notes
+//   * one thread per Gaussian, grid sized in whole waves; the forward kernel is a single streaming pass
+//     (HBM-bound: ~332 B in / ~250 B out per Gaussian at the headline config) that ALSO
+//       - zero-fills out_observe (no separate memset),
+//       - emits the 32-bit depth sort key (0xFFFFFFFF for culled splats) for the depth-major presort,
+//       - packs every attribute the tile renderers need into ONE sector-aligned record per Gaussian
+//         ({xy, conic, opacity} + all blended channels), so that the per-tile staging is a single
+//         contiguous bulk copy per list entry instead of 5 scattered gathers.
+//   * the backward kernel fuses the reference's computeCov2DCUDA + preprocessCUDA launches and writes
+//     every gradient row exactly once (zeros for culled splats), which removes ~400 MB of separate
+//     zero-fill traffic at 1M Gaussians.
+//   * arithmetic that feeds radii / tile rects / depth keys keeps the reference's scalar expression
+//     order (including the fp64 island in ndc_to_pix) because those outputs are compared bit-exactly.
+#include "kernels.cuh"
+
+namespace lsx {
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+
+// world covariance from (scale, un-normalised quaternion); forward.cu:119-152
+__device__ __forceinline__ void world_covariance(const float3 scale, const float mod, const float4 q, float* cov6) {
+    Mat3 S;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) S.m[c][r] = 0.0f;
+    S.m[0][0] = mod * scale.x;
+    S.m[1][1] = mod * scale.y;
+    S.m[2][2] = mod * scale.z;
+
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    Mat3 R;
+    R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+    R.m[0][1] = 2.f * (x * y - r * z);
+    R.m[0][2] = 2.f * (x * z + r * y);
+    R.m[1][0] = 2.f * (x * y + r * z);
+    R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+    R.m[1][2] = 2.f * (y * z - r * x);
+    R.m[2][0] = 2.f * (x * z - r * y);
+    R.m[2][1] = 2.f * (y * z + r * x);
+    R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+
+    const Mat3 Mx = mat3_mul(S, R);
+    const Mat3 Sigma = mat3_mul(mat3_transpose(Mx), Mx);
+    cov6[0] = Sigma.m[0][0];
+    cov6[1] = Sigma.m[0][1];
+    cov6[2] = Sigma.m[0][2];
+    cov6[3] = Sigma.m[1][1];
+    cov6[4] = Sigma.m[1][2];
+    cov6[5] = Sigma.m[2][2];
+}
+
+struct Cov2DFrame {  // intermediates shared by forward and backward EWA projection
+    Mat3 T;          // W * J
+    Mat3 V;          // symmetric world covariance
+    float3 t;        // clamped view-space mean
+    float txtz, tytz, limx, limy;
+};
+
+__device__ __forceinline__ void ewa_frame(const float3 mean, const float fx, const float fy, const float tan_fovx,
+                                          const float tan_fovy, const float* cov6, const float* __restrict__ view,
+                                          Cov2DFrame& f) {
+    float3 t = xform_point_4x3(mean, view);
+    f.limx = 1.3f * tan_fovx;
+    f.limy = 1.3f * tan_fovy;
+    f.txtz = t.x / t.z;
+    f.tytz = t.y / t.z;
+    t.x = fminf(f.limx, fmaxf(-f.limx, f.txtz)) * t.z;
+    t.y = fminf(f.limy, fmaxf(-f.limy, f.tytz)) * t.z;
+    f.t = t;
+
+    Mat3 J;
+    J.m[0][0] = fx / t.z;
+    J.m[0][1] = 0.0f;
+    J.m[0][2] = -(fx * t.x) / (t.z * t.z);
+    J.m[1][0] = 0.0f;
+    J.m[1][1] = fy / t.z;
+    J.m[1][2] = -(fy * t.y) / (t.z * t.z);
+    J.m[2][0] = 0.0f;
+    J.m[2][1] = 0.0f;
+    J.m[2][2] = 0.0f;
+
+    Mat3 Wm;
+    Wm.m[0][0] = view[0]; Wm.m[0][1] = view[4]; Wm.m[0][2] = view[8];
+    Wm.m[1][0] = view[1]; Wm.m[1][1] = view[5]; Wm.m[1][2] = view[9];
+    Wm.m[2][0] = view[2]; Wm.m[2][1] = view[6]; Wm.m[2][2] = view[10];
+
+    f.T = mat3_mul(Wm, J);
+
+    f.V.m[0][0] = cov6[0]; f.V.m[0][1] = cov6[1]; f.V.m[0][2] = cov6[2];
+    f.V.m[1][0] = cov6[1]; f.V.m[1][1] = cov6[3]; f.V.m[1][2] = cov6[4];
+    f.V.m[2][0] = cov6[2]; f.V.m[2][1] = cov6[4]; f.V.m[2][2] = cov6[5];
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwdParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+
+    // defaults for a culled splat
+    p.radii[idx] = 0;
+    p.tiles_touched[idx] = 0;
+    p.out_observe[idx] = 0;
+    p.depth_keys[idx] = 0xFFFFFFFFu;
+
+    const float3 pw = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    const float3 pv = xform_point_4x3(pw, p.view);
+    if (pv.z <= 0.2f) {
+        if (p.prefiltered) {
+            printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+            __trap();
+        }
+        return;
+    }
+
+    const float4 ph = xform_point_4x4(pw, p.proj);
+    const float pw_inv = 1.0f / (ph.w + 0.0000001f);
+    const float3 pn = make_float3(ph.x * pw_inv, ph.y * pw_inv, ph.z * pw_inv);
+
+    float cov6[6];
+    if (p.cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) cov6[i] = p.cov3D_precomp[6 * idx + i];
+    } else {
+        const float3 sc = make_float3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
+        const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+        world_covariance(sc, p.scale_modifier, q, cov6);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) p.cov3D[6 * idx + i] = cov6[i];
+    }
+
+    Cov2DFrame fr;
+    ewa_frame(pw, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, cov6, p.view, fr);
+    const Mat3 c2 = mat3_mul(mat3_mul(mat3_transpose(fr.T), mat3_transpose(fr.V)), fr.T);
+    const float cxx = c2.m[0][0] + 0.3f;
+    const float cxy = c2.m[0][1];
+    const float cyy = c2.m[1][1] + 0.3f;
+
+    const float det = (cxx * cyy - cxy * cxy);
+    if (det == 0.0f) return;
+    const float det_inv = 1.f / det;
+    const float3 conic = make_float3(cyy * det_inv, -cxy * det_inv, cxx * det_inv);
+
+    const float mid = 0.5f * (cxx + cyy);
+    const float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+    const float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+    const float2 pix = make_float2(ndc_to_pix(pn.x, p.W), ndc_to_pix(pn.y, p.H));
+    uint2 rmin, rmax;
+    tile_rect(pix, (int)my_radius, rmin, rmax, p.grid_x, p.grid_y);
+    const uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
+    if (ntiles == 0) return;
+
+    // colour: SH evaluation (degrees 0..3) or the caller's precomputed RGB
+    float rgb[3];
+    if (p.colors_precomp == nullptr) {
+        const float dx0 = pw.x - p.campos[0], dy0 = pw.y - p.campos[1], dz0 = pw.z - p.campos[2];
+        const float len = sqrtf(dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
+        const float x = dx0 / len, y = dy0 / len, z = dz0 / len;
+        const float* sh = p.shs + (size_t)idx * p.M * 3;
+        unsigned clamp_bits = 0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float res = kSH0 * sh[c];
+            if (p.D > 0) {
+                res = res - kSH1 * y * sh[3 + c] + kSH1 * z * sh[6 + c] - kSH1 * x * sh[9 + c];
+                if (p.D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z;
+                    const float xy = x * y, yz = y * z, xz = x * z;
+                    res = res + kSH2[0] * xy * sh[12 + c] + kSH2[1] * yz * sh[15 + c] +
+                          kSH2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + kSH2[3] * xz * sh[21 + c] +
+                          kSH2[4] * (xx - yy) * sh[24 + c];
+                    if (p.D > 2) {
+                        res = res + kSH3[0] * y * (3.0f * xx - yy) * sh[27 + c] + kSH3[1] * xy * z * sh[30 + c] +
+                              kSH3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                              kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                              kSH3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + kSH3[5] * z * (xx - yy) * sh[42 + c] +
+                              kSH3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                    }
+                }
+            }
+            res += 0.5f;
+            if (res < 0) clamp_bits |= (1u << c);
+            rgb[c] = fmaxf(res, 0.0f);
+        }
+        p.clamped[idx] = (uint8_t)clamp_bits;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p.rgb[3 * idx + c] = rgb[c];
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rgb[c] = p.colors_precomp[3 * idx + c];
+    }
+
+    const float opacity = p.opacities[idx];
+    p.depths[idx] = pv.z;
+    p.depth_keys[idx] = __float_as_uint(pv.z);
+    p.radii[idx] = (int)my_radius;
+    p.means2D[idx] = pix;
+    p.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacity);
+    p.tiles_touched[idx] = ntiles;
+
+    // packed blend record (sector aligned): head + channels
+    float* rec = p.records + (size_t)idx * p.rec_stride;
+    reinterpret_cast<float4*>(rec)[0] = make_float4(pix.x, pix.y, conic.x, conic.y);
+    reinterpret_cast<float4*>(rec)[1] = make_float4(conic.z, opacity, 0.f, 0.f);
+    float* ch = rec + REC_HEAD;
+    int c = 0;
+    ch[c++] = rgb[0];
+    ch[c++] = rgb[1];
+    ch[c++] = rgb[2];
+    if (p.include_feature) {
+        const float* lf = p.language_feature + (size_t)idx * p.F;
+        for (int i = 0; i < p.F; ++i) ch[c++] = lf[i];
+        const float* li = p.language_feature_instance + (size_t)idx * p.Fi;
+        for (int i = 0; i < p.Fi; ++i) ch[c++] = li[i];
+    }
+    if (p.render_geo) {
+        const float* am = p.all_map + (size_t)idx * 5;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) ch[c++] = am[i];
+    }
+    for (; c < p.rec_stride - REC_HEAD; ++c) ch[c] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (K8 + K9 fused): dL/dconic, dL/dmean2D, dL/dcolor  ->  dL/d{mean3D, cov3D, sh, scale, rot}
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwdParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+
+    const int n_sh = p.M * 3;
+    float* g_sh = p.dL_dsh ? p.dL_dsh + (size_t)idx * n_sh : nullptr;
+
+    if (!(p.radii[idx] > 0)) {
+        // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
+        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g_sh)
+            for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
+        return;
+    }
+
+    const float3 mean = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    const float* cov6 = (p.cov3D_precomp ? p.cov3D_precomp : p.cov3D) + 6 * (size_t)idx;
+    float c6[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) c6[i] = cov6[i];
+
+    // ---- part 1: conic gradient through the 2D covariance (backward.cu:144-274) -----------------
+    const float3 g_conic = make_float3(p.dL_dconic[4 * idx], p.dL_dconic[4 * idx + 1], p.dL_dconic[4 * idx + 3]);
+    Cov2DFrame fr;
+    ewa_frame(mean, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, c6, p.view, fr);
+    const Mat3& T = fr.T;
+    const Mat3& V = fr.V;
+    const float gate_x = (fr.txtz < -fr.limx || fr.txtz > fr.limx) ? 0.f : 1.f;
+    const float gate_y = (fr.tytz < -fr.limy || fr.tytz > fr.limy) ? 0.f : 1.f;
+
+    const Mat3 c2 = mat3_mul(mat3_mul(mat3_transpose(T), mat3_transpose(V)), T);
+    const float a = c2.m[0][0] + 0.3f;
+    const float b = c2.m[0][1];
+    const float c = c2.m[1][1] + 0.3f;
+    const float denom = a * c - b * b;
+    float g_a = 0.f, g_b = 0.f, g_c = 0.f;
+    const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+
+    float g_cov[6];
+    if (denom2inv != 0) {
+        g_a = denom2inv * (-c * c * g_conic.x + 2 * b * c * g_conic.y + (denom - a * c) * g_conic.z);
+        g_c = denom2inv * (-a * a * g_conic.z + 2 * a * b * g_conic.y + (denom - a * c) * g_conic.x);
+        g_b = denom2inv * 2 * (b * c * g_conic.x - (denom + 2 * b * b) * g_conic.y + a * b * g_conic.z);
+
+        // diagonal world-covariance entries
+        g_cov[0] = (T.m[0][0] * T.m[0][0] * g_a + T.m[0][0] * T.m[1][0] * g_b + T.m[1][0] * T.m[1][0] * g_c);
+        g_cov[3] = (T.m[0][1] * T.m[0][1] * g_a + T.m[0][1] * T.m[1][1] * g_b + T.m[1][1] * T.m[1][1] * g_c);
+        g_cov[5] = (T.m[0][2] * T.m[0][2] * g_a + T.m[0][2] * T.m[1][2] * g_b + T.m[1][2] * T.m[1][2] * g_c);
+        // off-diagonal entries appear twice in the symmetric matrix
+        g_cov[1] = 2 * T.m[0][0] * T.m[0][1] * g_a + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * g_b +
+                   2 * T.m[1][0] * T.m[1][1] * g_c;
+        g_cov[2] = 2 * T.m[0][0] * T.m[0][2] * g_a + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * g_b +
+                   2 * T.m[1][0] * T.m[1][2] * g_c;
+        g_cov[4] = 2 * T.m[0][2] * T.m[0][1] * g_a + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * g_b +
+                   2 * T.m[1][1] * T.m[1][2] * g_c;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) g_cov[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = g_cov[i];
+
+    // gradient w.r.t. the upper 2x3 block of T
+    float tv0[3], tv1[3];  // (row of T) . V columns
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        tv0[k] = T.m[0][0] * V.m[k][0] + T.m[0][1] * V.m[k][1] + T.m[0][2] * V.m[k][2];
+        tv1[k] = T.m[1][0] * V.m[k][0] + T.m[1][1] * V.m[k][1] + T.m[1][2] * V.m[k][2];
+    }
+    const float g_T00 = 2 * tv0[0] * g_a + tv1[0] * g_b;
+    const float g_T01 = 2 * tv0[1] * g_a + tv1[1] * g_b;
+    const float g_T02 = 2 * tv0[2] * g_a + tv1[2] * g_b;
+    const float g_T10 = 2 * tv1[0] * g_c + tv0[0] * g_b;
+    const float g_T11 = 2 * tv1[1] * g_c + tv0[1] * g_b;
+    const float g_T12 = 2 * tv1[2] * g_c + tv0[2] * g_b;
+
+    // T = W * J  ->  the four non-constant Jacobian entries
+    const float* vm = p.view;
+    const float g_J00 = vm[0] * g_T00 + vm[4] * g_T01 + vm[8] * g_T02;
+    const float g_J02 = vm[2] * g_T00 + vm[6] * g_T01 + vm[10] * g_T02;
+    const float g_J11 = vm[1] * g_T10 + vm[5] * g_T11 + vm[9] * g_T12;
+    const float g_J12 = vm[2] * g_T10 + vm[6] * g_T11 + vm[10] * g_T12;
+
+    const float tz = 1.f / fr.t.z;
+    const float tz2 = tz * tz;
+    const float tz3 = tz2 * tz;
+    const float g_tx = gate_x * -p.focal_x * tz2 * g_J02;
+    const float g_ty = gate_y * -p.focal_y * tz2 * g_J12;
+    const float g_tz = -p.focal_x * tz2 * g_J00 - p.focal_y * tz2 * g_J11 + (2 * p.focal_x * fr.t.x) * tz3 * g_J02 +
+                       (2 * p.focal_y * fr.t.y) * tz3 * g_J12;
+
+    // t = view * mean  ->  multiply by the transposed rotation part
+    float3 g_mean = make_float3(vm[0] * g_tx + vm[1] * g_ty + vm[2] * g_tz, vm[4] * g_tx + vm[5] * g_ty + vm[6] * g_tz,
+                                vm[8] * g_tx + vm[9] * g_ty + vm[10] * g_tz);
+
+    // ---- part 2: screen-space mean gradient through the projection (backward.cu:370-387) ---------
+    {
+        const float* pr = p.proj;
+        const float4 mh = xform_point_4x4(mean, pr);
+        const float mw = 1.0f / (mh.w + 0.0000001f);
+        const float mul1 = (pr[0] * mean.x + pr[4] * mean.y + pr[8] * mean.z + pr[12]) * mw * mw;
+        const float mul2 = (pr[1] * mean.x + pr[5] * mean.y + pr[9] * mean.z + pr[13]) * mw * mw;
+        const float gx = p.dL_dmean2D[3 * idx], gy = p.dL_dmean2D[3 * idx + 1];
+        float3 d;
+        d.x = (pr[0] * mw - pr[3] * mul1) * gx + (pr[1] * mw - pr[3] * mul2) * gy;
+        d.y = (pr[4] * mw - pr[7] * mul1) * gx + (pr[5] * mw - pr[7] * mul2) * gy;
+        d.z = (pr[8] * mw - pr[11] * mul1) * gx + (pr[9] * mw - pr[11] * mul2) * gy;
+        g_mean.x += d.x;
+        g_mean.y += d.y;
+        g_mean.z += d.z;
+    }
+
+    // ---- part 3: SH colour gradient (backward.cu:20-139) ------------------------------------------
+    if (p.shs != nullptr) {
+        const float ox = mean.x - p.campos[0], oy = mean.y - p.campos[1], oz = mean.z - p.campos[2];
+        const float len = sqrtf(ox * ox + oy * oy + oz * oz);
+        const float x = ox / len, y = oy / len, z = oz / len;
+        const float* sh = p.shs + (size_t)idx * n_sh;
+        const unsigned cl = p.clamped[idx];
+        float gc[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gc[k] = p.dL_dcolor[3 * idx + k] * (((cl >> k) & 1u) ? 0.f : 1.f);
+
+        // basis values (the derivative of RGB w.r.t. each coefficient) and d(RGB)/d(dir)
+        float basis[16];
+        float ddx[3] = {0.f, 0.f, 0.f}, ddy[3] = {0.f, 0.f, 0.f}, ddz[3] = {0.f, 0.f, 0.f};
+        int nb = 1;
+        basis[0] = kSH0;
+        if (p.D > 0) {
+            nb = 4;
+            basis[1] = -kSH1 * y;
+            basis[2] = kSH1 * z;
+            basis[3] = -kSH1 * x;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                ddx[k] = -kSH1 * sh[9 + k];
+                ddy[k] = -kSH1 * sh[3 + k];
+                ddz[k] = kSH1 * sh[6 + k];
+            }
+            if (p.D > 1) {
+                nb = 9;
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                basis[4] = kSH2[0] * xy;
+                basis[5] = kSH2[1] * yz;
+                basis[6] = kSH2[2] * (2.f * zz - xx - yy);
+                basis[7] = kSH2[3] * xz;
+                basis[8] = kSH2[4] * (xx - yy);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    ddx[k] += kSH2[0] * y * sh[12 + k] + kSH2[2] * 2.f * -x * sh[18 + k] + kSH2[3] * z * sh[21 + k] +
+                              kSH2[4] * 2.f * x * sh[24 + k];
+                    ddy[k] += kSH2[0] * x * sh[12 + k] + kSH2[1] * z * sh[15 + k] + kSH2[2] * 2.f * -y * sh[18 + k] +
+                              kSH2[4] * 2.f * -y * sh[24 + k];
+                    ddz[k] += kSH2[1] * y * sh[15 + k] + kSH2[2] * 2.f * 2.f * z * sh[18 + k] + kSH2[3] * x * sh[21 + k];
+                }
+                if (p.D > 2) {
+                    nb = 16;
+                    basis[9] = kSH3[0] * y * (3.f * xx - yy);
+                    basis[10] = kSH3[1] * xy * z;
+                    basis[11] = kSH3[2] * y * (4.f * zz - xx - yy);
+                    basis[12] = kSH3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                    basis[13] = kSH3[4] * x * (4.f * zz - xx - yy);
+                    basis[14] = kSH3[5] * z * (xx - yy);
+                    basis[15] = kSH3[6] * x * (xx - 3.f * yy);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        ddx[k] += (kSH3[0] * sh[27 + k] * 3.f * 2.f * xy + kSH3[1] * sh[30 + k] * yz +
+                                   kSH3[2] * sh[33 + k] * -2.f * xy + kSH3[3] * sh[36 + k] * -3.f * 2.f * xz +
+                                   kSH3[4] * sh[39 + k] * (-3.f * xx + 4.f * zz - yy) + kSH3[5] * sh[42 + k] * 2.f * xz +
+                                   kSH3[6] * sh[45 + k] * 3.f * (xx - yy));
+                        ddy[k] += (kSH3[0] * sh[27 + k] * 3.f * (xx - yy) + kSH3[1] * sh[30 + k] * xz +
+                                   kSH3[2] * sh[33 + k] * (-3.f * yy + 4.f * zz - xx) +
+                                   kSH3[3] * sh[36 + k] * -3.f * 2.f * yz + kSH3[4] * sh[39 + k] * -2.f * xy +
+                                   kSH3[5] * sh[42 + k] * -2.f * yz + kSH3[6] * sh[45 + k] * -3.f * 2.f * xy);
+                        ddz[k] += (kSH3[1] * sh[30 + k] * xy + kSH3[2] * sh[33 + k] * 4.f * 2.f * yz +
+                                   kSH3[3] * sh[36 + k] * 3.f * (2.f * zz - xx - yy) +
+                                   kSH3[4] * sh[39 + k] * 4.f * 2.f * xz + kSH3[5] * sh[42 + k] * (xx - yy));
+                    }
+                }
+            }
+        }
+        for (int j = 0; j < p.M; ++j) {
+            const float bj = (j < nb) ? basis[j < 16 ? j : 15] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g_sh[3 * j + k] = (j < nb) ? bj * gc[k] : 0.f;
+        }
+
+        // direction gradient, then through the normalisation dir = v / |v|
+        const float gdx = ddx[0] * gc[0] + ddx[1] * gc[1] + ddx[2] * gc[2];
+        const float gdy = ddy[0] * gc[0] + ddy[1] * gc[1] + ddy[2] * gc[2];
+        const float gdz = ddz[0] * gc[0] + ddz[1] * gc[1] + ddz[2] * gc[2];
+        const float sum2 = ox * ox + oy * oy + oz * oz;
+        const float inv32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        g_mean.x += ((+sum2 - ox * ox) * gdx - oy * ox * gdy - oz * ox * gdz) * inv32;
+        g_mean.y += (-ox * oy * gdx + (sum2 - oy * oy) * gdy - oz * oy * gdz) * inv32;
+        g_mean.z += (-ox * oz * gdx - oy * oz * gdy + (sum2 - oz * oz) * gdz) * inv32;
+    } else if (g_sh) {
+        for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
+    }
+
+    p.dL_dmeans3D[3 * idx + 0] = g_mean.x;
+    p.dL_dmeans3D[3 * idx + 1] = g_mean.y;
+    p.dL_dmeans3D[3 * idx + 2] = g_mean.z;
+
+    // ---- part 4: world covariance -> scale / rotation (backward.cu:278-341) ------------------------
+    if (p.scales != nullptr) {
+        const float3 sc = make_float3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
+        const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+        const float r = q.x, x = q.y, y = q.z, z = q.w;
+        Mat3 R;
+        R.m[0][0] = 1.f - 2.f * (y * y + z * z);
+        R.m[0][1] = 2.f * (x * y - r * z);
+        R.m[0][2] = 2.f * (x * z + r * y);
+        R.m[1][0] = 2.f * (x * y + r * z);
+        R.m[1][1] = 1.f - 2.f * (x * x + z * z);
+        R.m[1][2] = 2.f * (y * z - r * x);
+        R.m[2][0] = 2.f * (x * z - r * y);
+        R.m[2][1] = 2.f * (y * z + r * x);
+        R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+        const float3 s = make_float3(p.scale_modifier * sc.x, p.scale_modifier * sc.y, p.scale_modifier * sc.z);
+        Mat3 S;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) S.m[cc][rr] = 0.f;
+        S.m[0][0] = s.x;
+        S.m[1][1] = s.y;
+        S.m[2][2] = s.z;
+        const Mat3 Mx = mat3_mul(S, R);
+
+        Mat3 gS;  // symmetric dL/dSigma with halved off-diagonals
+        gS.m[0][0] = g_cov[0];        gS.m[0][1] = 0.5f * g_cov[1]; gS.m[0][2] = 0.5f * g_cov[2];
+        gS.m[1][0] = 0.5f * g_cov[1]; gS.m[1][1] = g_cov[3];        gS.m[1][2] = 0.5f * g_cov[4];
+        gS.m[2][0] = 0.5f * g_cov[2]; gS.m[2][1] = 0.5f * g_cov[4]; gS.m[2][2] = g_cov[5];
+
+        Mat3 M2;
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) M2.m[cc][rr] = 2.0f * Mx.m[cc][rr];
+        const Mat3 gM = mat3_mul(M2, gS);
+        const Mat3 Rt = mat3_transpose(R);
+        Mat3 gMt = mat3_transpose(gM);
+
+        p.dL_dscales[3 * idx + 0] = Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2];
+        p.dL_dscales[3 * idx + 1] = Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2];
+        p.dL_dscales[3 * idx + 2] = Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2];
+
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+            gMt.m[0][rr] *= s.x;
+            gMt.m[1][rr] *= s.y;
+            gMt.m[2][rr] *= s.z;
+        }
+        float4 gq;
+        gq.x = 2 * z * (gMt.m[0][1] - gMt.m[1][0]) + 2 * y * (gMt.m[2][0] - gMt.m[0][2]) + 2 * x * (gMt.m[1][2] - gMt.m[2][1]);
+        gq.y = 2 * y * (gMt.m[1][0] + gMt.m[0][1]) + 2 * z * (gMt.m[2][0] + gMt.m[0][2]) + 2 * r * (gMt.m[1][2] - gMt.m[2][1]) -
+               4 * x * (gMt.m[2][2] + gMt.m[1][1]);
+        gq.z = 2 * x * (gMt.m[1][0] + gMt.m[0][1]) + 2 * r * (gMt.m[2][0] - gMt.m[0][2]) + 2 * z * (gMt.m[1][2] + gMt.m[2][1]) -
+               4 * y * (gMt.m[2][2] + gMt.m[0][0]);
+        gq.w = 2 * r * (gMt.m[0][1] - gMt.m[1][0]) + 2 * x * (gMt.m[2][0] + gMt.m[0][2]) + 2 * y * (gMt.m[1][2] + gMt.m[2][1]) -
+               4 * z * (gMt.m[1][1] + gMt.m[0][0]);
+        reinterpret_cast<float4*>(p.dL_drotations)[idx] = gq;  // w.r.t. the raw (un-normalised) quaternion
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
+        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                                           const float* __restrict__ view, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float3 pw = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    const float3 pv = xform_point_4x3(pw, view);
+    present[idx] = pv.z > 0.2f ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, bool debug) {
+    if (p.P <= 0) return 0;
+    preprocess_fwd_kernel<<<ceil_div(p.P, 256), 256, 0, stream>>>(p);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
+}
+
+int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
+    if (p.P <= 0) return 0;
+    preprocess_bwd_kernel<<<ceil_div(p.P, 256), 256, 0, stream>>>(p);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, means3D, view, present);
+    LSX_KERNEL_OK(stream, false);
+    return 0;
+}
+
+}  // namespace lsx

@@ -1,0 +1,247 @@
+// sort.cu — device-wide exclusive scan and stable LSD radix sort of (u32 key, u32 value) pairs.
+//
+// These replace the reference's CUB calls on the hot path
+//   cub::DeviceScan::InclusiveSum        rasterizer_impl.cu:287
+//   cub::DeviceRadixSort::SortPairs      rasterizer_impl.cu:313-318 (64-bit tile|depth keys)
+//   cub::DeviceRadixSort::SortPairs      simple_knn.cu:210-213     (30-bit Morton codes)
+//
+// The 64-bit (tile << 32 | depth) sort of the reference is an LSD radix sort: the low 32 bits (depth)
+// are processed first, the tile bits last.  Because all duplicates of one Gaussian carry the same depth
+// and are emitted contiguously in index order, the depth passes can run on the P Gaussians BEFORE
+// duplication (4 passes over P pairs) and only the tile passes (ceil(bit/8), 2 at 1080p) have to touch
+// the R duplicated pairs; the sorted output is identical (see binning.cu).  Both stages use this one
+// 32-bit-key kernel, as does the Morton sort of the KNN initialisation.
+//
+// Pass structure (8-bit digits): per-block digit histogram -> exclusive scan (digit-major) -> stable
+// scatter.  In the scatter kernel each warp owns a contiguous 512-key segment and ranks its keys with
+// __match_any_sync against warp-private shared-memory counters; a 256-thread step turns the per-warp
+// counters into global positions.  No inter-block spinning anywhere (see B200_PROFILING.md on why).
+#include "kernels.cuh"
+
+namespace lsx {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kThreads * kItems;  // 4096 elements per block
+constexpr int kWarps = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------
+// scan
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& block_total) {
+    // returns the exclusive prefix of v over the block's threads
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t wsum = (lane < (int)(blockDim.x >> 5)) ? s_warp[lane] : 0;
+    uint32_t winc = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const uint32_t warp_off = __shfl_sync(kFull, winc - wsum, warp);
+    block_total = __shfl_sync(kFull, winc, (blockDim.x >> 5) - 1);
+    __syncthreads();
+    return warp_off + inc - v;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* __restrict__ in,
+                                                               const uint32_t* __restrict__ gather, int n,
+                                                               uint32_t* __restrict__ partials) {
+    __shared__ uint32_t s_warp[32];
+    const int base = blockIdx.x * kTile;
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = base + i * kThreads + threadIdx.x;
+        if (idx < n) sum += gather ? in[gather[idx]] : in[idx];
+    }
+    uint32_t total;
+    block_exclusive_scan(sum, s_warp, total);
+    if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* __restrict__ partials, int nb,
+                                                             uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_warp[32];
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const uint32_t v = idx < nb ? partials[idx] : 0;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, s_warp, total);
+        if (idx < nb) partials[idx] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __restrict__ in,
+                                                              const uint32_t* __restrict__ gather,
+                                                              uint32_t* __restrict__ out, int n,
+                                                              const uint32_t* __restrict__ partials) {
+    __shared__ uint32_t s_warp[32];
+    const int base = blockIdx.x * kTile + threadIdx.x * kItems;  // blocked arrangement
+    uint32_t v[kItems];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = base + i;
+        v[i] = idx < n ? (gather ? in[gather[idx]] : in[idx]) : 0;
+        sum += v[i];
+    }
+    uint32_t total;
+    uint32_t run = block_exclusive_scan(sum, s_warp, total) + partials[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = base + i;
+        if (idx < n) out[idx] = run;
+        run += v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix sort pass
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
+                                                              uint32_t mask, uint32_t* __restrict__ hist, int nb) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kTile;
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = base + i * kThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x <= mask) hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                 const uint32_t* __restrict__ vals_in,
+                                                                 uint32_t* __restrict__ keys_out,
+                                                                 uint32_t* __restrict__ vals_out, int n, int shift,
+                                                                 uint32_t mask, const uint32_t* __restrict__ offsets,
+                                                                 int nb) {
+    __shared__ uint32_t cnt[kWarps][256];
+    for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wbase = blockIdx.x * kTile + warp * (32 * kItems);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    uint32_t key[kItems];
+    uint32_t rank[kItems];
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        key[i] = idx < n ? keys_in[idx] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        const bool valid = idx < n;
+        const uint32_t d = valid ? ((key[i] >> shift) & mask) : 0x100u;
+        const uint32_t peers = __match_any_sync(kFull, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (lane == leader && valid) {
+            old = cnt[warp][d];
+            cnt[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(kFull, old, leader);
+        rank[i] = old + __popc(peers & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+    {
+        const uint32_t d = threadIdx.x;
+        if (d <= mask) {
+            uint32_t run = offsets[d * nb + blockIdx.x];
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t t = cnt[w][d];
+                cnt[w][d] = run;
+                run += t;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = wbase + i * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = (key[i] >> shift) & mask;
+            const uint32_t pos = cnt[warp][d] + rank[i];
+            keys_out[pos] = key[i];
+            vals_out[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+        }
+    }
+}
+
+}  // namespace
+
+size_t scan_temp_bytes(int n) { return align_up((size_t)ceil_div(n > 0 ? n : 1, kTile) * sizeof(uint32_t), 256); }
+
+int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out, int n, uint32_t* total, void* temp,
+                       cudaStream_t stream, bool debug) {
+    if (n <= 0) {
+        if (total) LSX_CUDA_OK(cudaMemsetAsync(total, 0, sizeof(uint32_t), stream));
+        return 0;
+    }
+    const int nb = ceil_div(n, kTile);
+    uint32_t* partials = static_cast<uint32_t*>(temp);
+    scan_reduce_kernel<<<nb, kThreads, 0, stream>>>(in, gather, n, partials);
+    LSX_KERNEL_OK(stream, debug);
+    scan_partials_kernel<<<1, 1024, 0, stream>>>(partials, nb, total);
+    LSX_KERNEL_OK(stream, debug);
+    scan_apply_kernel<<<nb, kThreads, 0, stream>>>(in, gather, out, n, partials);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
+}
+
+size_t radix_sort_temp_bytes(int n) {
+    const int nb = ceil_div(n > 0 ? n : 1, kTile);
+    return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + scan_temp_bytes(256 * nb);
+}
+
+int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_bit, int end_bit, bool identity_vals,
+                         void* temp, int* result_buf, cudaStream_t stream, bool debug) {
+    *result_buf = 0;
+    if (n <= 0) return 0;
+    const int nb = ceil_div(n, kTile);
+    uint32_t* hist = static_cast<uint32_t*>(temp);
+    void* scan_temp = static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256);
+    int cur = 0;
+    bool first = true;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
+        const uint32_t mask = (1u << bits) - 1u;
+        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, nb);
+        LSX_KERNEL_OK(stream, debug);
+        int rc = exclusive_scan_u32(hist, nullptr, hist, (int)(mask + 1) * nb, nullptr, scan_temp, stream, debug);
+        if (rc) return rc;
+        const uint32_t* vin = (first && identity_vals) ? nullptr : vals[cur];
+        radix_scatter_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+                                                          hist, nb);
+        LSX_KERNEL_OK(stream, debug);
+        cur ^= 1;
+        first = false;
+    }
+    *result_buf = cur;
+    return 0;
+}
+
+}  // namespace lsx

@@ -1,0 +1,121 @@
+"""ctypes binding of liblsx_b200.so (C ABI: include/lsx_rasterizer.h).
+
+This is the ONLY compute path: if the library is missing or fails to load, importing raises — there is
+no CPU / eager fallback.  PyTorch is used purely for device memory and stream handles.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_size_t, c_uint64, c_void_p
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("LSX_B200_LIB", os.path.join(_PKG_DIR, "liblsx_b200.so"))
+
+ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
+
+ABI_VERSION = 1
+MAX_BLEND_CHANNELS = 40
+
+
+class ForwardArgs(ctypes.Structure):
+    _fields_ = [
+        ("P", c_int32), ("D", c_int32), ("M", c_int32), ("W", c_int32), ("H", c_int32),
+        ("F", c_int32), ("Fi", c_int32),
+        ("tanfovx", c_float), ("tanfovy", c_float), ("scale_modifier", c_float),
+        ("prefiltered", c_int32), ("render_geo", c_int32), ("debug", c_int32), ("include_feature", c_int32),
+        ("background", c_void_p), ("means3D", c_void_p), ("shs", c_void_p), ("colors_precomp", c_void_p),
+        ("language_feature", c_void_p), ("language_feature_instance", c_void_p), ("opacities", c_void_p),
+        ("scales", c_void_p), ("rotations", c_void_p), ("cov3D_precomp", c_void_p), ("all_map", c_void_p),
+        ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
+        ("out_color", c_void_p), ("out_language_feature", c_void_p), ("out_language_feature_instance", c_void_p),
+        ("radii", c_void_p), ("out_observe", c_void_p), ("out_all_map", c_void_p), ("out_plane_depth", c_void_p),
+        ("geom_alloc", ALLOC_FN), ("geom_user", c_void_p),
+        ("binning_alloc", ALLOC_FN), ("binning_user", c_void_p),
+        ("image_alloc", ALLOC_FN), ("image_user", c_void_p),
+        ("stream", c_void_p),
+    ]
+
+
+class BackwardArgs(ctypes.Structure):
+    _fields_ = [
+        ("P", c_int32), ("D", c_int32), ("M", c_int32), ("W", c_int32), ("H", c_int32),
+        ("F", c_int32), ("Fi", c_int32), ("R", c_int32),
+        ("tanfovx", c_float), ("tanfovy", c_float), ("scale_modifier", c_float),
+        ("render_geo", c_int32), ("debug", c_int32), ("include_feature", c_int32),
+        ("background", c_void_p), ("means3D", c_void_p), ("shs", c_void_p), ("colors_precomp", c_void_p),
+        ("language_feature", c_void_p), ("language_feature_instance", c_void_p), ("all_map", c_void_p),
+        ("scales", c_void_p), ("rotations", c_void_p), ("cov3D_precomp", c_void_p),
+        ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p), ("radii", c_void_p),
+        ("out_all_map", c_void_p), ("geom_buffer", c_void_p), ("binning_buffer", c_void_p), ("image_buffer", c_void_p),
+        ("dL_dout_color", c_void_p), ("dL_dout_language_feature", c_void_p),
+        ("dL_dout_language_feature_instance", c_void_p), ("dL_dout_all_map", c_void_p),
+        ("dL_dout_plane_depth", c_void_p),
+        ("dL_dmeans2D", c_void_p), ("dL_dmeans2D_abs", c_void_p), ("dL_dconic", c_void_p), ("dL_dopacity", c_void_p),
+        ("dL_dcolors", c_void_p), ("dL_dlanguage_feature", c_void_p), ("dL_dlanguage_feature_instance", c_void_p),
+        ("dL_dmeans3D", c_void_p), ("dL_dcov3D", c_void_p), ("dL_dsh", c_void_p), ("dL_dscales", c_void_p),
+        ("dL_drotations", c_void_p), ("dL_dall_map", c_void_p),
+        ("stream", c_void_p),
+    ]
+
+
+class ScratchLayout(ctypes.Structure):
+    _fields_ = [
+        ("depths", c_size_t), ("clamped", c_size_t), ("means2D", c_size_t), ("cov3D", c_size_t),
+        ("conic_opacity", c_size_t), ("rgb", c_size_t), ("tiles_touched", c_size_t), ("records", c_size_t),
+        ("record_stride", c_int32), ("geom_bytes", c_size_t),
+        ("final_T", c_size_t), ("n_contrib", c_size_t), ("ranges", c_size_t), ("image_bytes", c_size_t),
+        ("point_list", c_size_t), ("binning_bytes", c_size_t),
+    ]
+
+
+# every symbol include/lsx_rasterizer.h declares: name -> (restype, argtypes)
+EXPORTS = {
+    "lsx_rasterize_forward": (c_int32, [POINTER(ForwardArgs), POINTER(c_int32)]),
+    "lsx_rasterize_backward": (c_int32, [POINTER(BackwardArgs)]),
+    "lsx_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsx_knn_mean_dist2": (c_int32, [c_int32, c_void_p, c_void_p, ALLOC_FN, c_void_p, c_void_p]),
+    "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
+    "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p]),
+    "lsx_kernel_launch_count": (c_uint64, []),
+    "lsx_last_error": (c_char_p, []),
+    "lsx_abi_version": (c_int32, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle.  Raises if the CUDA library is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library has not been built "
+            "(run `python -c 'import __graft_entry__ as g; g.build()'` at the repo root). "
+            "There is no CPU fallback for this operator."
+        )
+    lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError here means header and library disagree
+        fn.restype = restype
+        fn.argtypes = argtypes
+    ver = lib.lsx_abi_version()
+    if ver != ABI_VERSION:
+        raise ImportError(f"liblsx_b200.so ABI version {ver} != binding version {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().lsx_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+def kernel_launch_count():
+    return int(load().lsx_kernel_launch_count())
