@@ -102,6 +102,24 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
     rect_max.y = min(grid_y, (uint32_t)max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)));
 }
 
+// Gaussian falloff exponent and opacity, with the exact operation sequence the reference's kernels execute
+// (SASS of forward.cu:363 / backward.cu:564 compiled by nvcc 12.9 for sm_100a):
+//   qz = (dy*cz)*dy ; qx = dx*cx ; cross = (dx*cy)*dy ; sum = fma(dx, qx, qz) ; power = fma(sum, -0.5, -cross)
+// Written with explicit round-to-nearest intrinsics so that the compiler cannot pick another contraction:
+// alpha / T thresholds (1/255, 1e-4, 0.5) then flip for exactly the same (pixel, Gaussian) pairs, which makes
+// n_contrib, final_T and out_observe reproducible bit for bit.
+__device__ __forceinline__ float splat_power(const float cx, const float cy, const float cz, const float dx,
+                                             const float dy) {
+    const float qz = __fmul_rn(__fmul_rn(dy, cz), dy);
+    const float qx = __fmul_rn(dx, cx);
+    const float cross = __fmul_rn(__fmul_rn(dx, cy), dy);
+    const float sum = __fmaf_rn(dx, qx, qz);
+    return __fmaf_rn(sum, -0.5f, -cross);
+}
+__device__ __forceinline__ float splat_alpha(const float opacity, const float gauss) {
+    return fminf(0.99f, __fmul_rn(opacity, gauss));
+}
+
 // real spherical-harmonics constants, degrees 0..3 (auxiliary.h:22-39)
 __device__ constexpr float kSH0 = 0.28209479177387814f;
 __device__ constexpr float kSH1 = 0.4886025119029199f;

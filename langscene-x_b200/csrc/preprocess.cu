@@ -166,31 +166,67 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwd
     float rgb[3];
     if (p.colors_precomp == nullptr) {
         const float dx0 = pw.x - p.campos[0], dy0 = pw.y - p.campos[1], dz0 = pw.z - p.campos[2];
-        const float len = sqrtf(dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
+        // Operation order pinned with explicit intrinsics to the sequence nvcc 12.9 emits for the reference's
+        // computeColorFromSH on sm_100a (which products are fused into FMAs is otherwise the compiler's
+        // choice), so the packed colour is reproduced bit for bit.
+        const float len = sqrtf(__fmaf_rn(dz0, dz0, __fmaf_rn(dx0, dx0, __fmul_rn(dy0, dy0))));
         const float x = dx0 / len, y = dy0 / len, z = dz0 / len;
         const float* sh = p.shs + (size_t)idx * p.M * 3;
         unsigned clamp_bits = 0;
+        // direction polynomials shared by the three colour channels
+        float b1y = 0.f, b1z = 0.f, b1x = 0.f, b4 = 0.f, b5 = 0.f, b6 = 0.f, b7 = 0.f, b8 = 0.f;
+        float b9 = 0.f, b10 = 0.f, b11 = 0.f, b12 = 0.f, b13 = 0.f, b14 = 0.f, b15 = 0.f;
+        if (p.D > 0) {
+            b1y = __fmul_rn(y, kSH1);
+            b1z = __fmul_rn(z, kSH1);
+            b1x = __fmul_rn(x, kSH1);
+            if (p.D > 1) {
+                const float xy = __fmul_rn(y, x), yz = __fmul_rn(z, y), xz = __fmul_rn(z, x);
+                const float zz = __fmul_rn(z, z), xx = __fmul_rn(x, x), yy = __fmul_rn(y, y);
+                const float zz2 = __fadd_rn(zz, zz);
+                const float xx_yy = __fadd_rn(xx, -yy);
+                b4 = __fmul_rn(xy, kSH2[0]);
+                b5 = __fmul_rn(yz, kSH2[1]);
+                b6 = __fmul_rn(__fadd_rn(-yy, __fadd_rn(-xx, zz2)), kSH2[2]);
+                b7 = __fmul_rn(xz, kSH2[3]);
+                b8 = __fmul_rn(xx_yy, kSH2[4]);
+                if (p.D > 2) {
+                    const float q4 = __fadd_rn(-yy, __fmaf_rn(zz, 4.0f, -xx));  // 4zz - xx - yy
+                    b9 = __fmul_rn(__fmul_rn(y, kSH3[0]), __fmaf_rn(xx, 3.0f, -yy));
+                    b10 = __fmul_rn(__fmul_rn(xy, kSH3[1]), z);
+                    b11 = __fmul_rn(__fmul_rn(y, kSH3[2]), q4);
+                    b12 = __fmul_rn(__fmul_rn(z, kSH3[3]), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+                    b13 = __fmul_rn(q4, __fmul_rn(x, kSH3[4]));
+                    b14 = __fmul_rn(xx_yy, __fmul_rn(z, kSH3[5]));
+                    b15 = __fmul_rn(__fmul_rn(x, kSH3[6]), __fmaf_rn(yy, -3.0f, xx));
+                }
+            }
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            float res = kSH0 * sh[c];
+            float res = __fmul_rn(sh[c], kSH0);
             if (p.D > 0) {
-                res = res - kSH1 * y * sh[3 + c] + kSH1 * z * sh[6 + c] - kSH1 * x * sh[9 + c];
+                res = __fmaf_rn(-b1y, sh[3 + c], res);
+                res = __fmaf_rn(b1z, sh[6 + c], res);
+                res = __fmaf_rn(-b1x, sh[9 + c], res);
                 if (p.D > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z;
-                    const float xy = x * y, yz = y * z, xz = x * z;
-                    res = res + kSH2[0] * xy * sh[12 + c] + kSH2[1] * yz * sh[15 + c] +
-                          kSH2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + kSH2[3] * xz * sh[21 + c] +
-                          kSH2[4] * (xx - yy) * sh[24 + c];
+                    res = __fmaf_rn(b4, sh[12 + c], res);
+                    res = __fmaf_rn(b5, sh[15 + c], res);
+                    res = __fmaf_rn(b6, sh[18 + c], res);
+                    res = __fmaf_rn(b7, sh[21 + c], res);
+                    res = __fmaf_rn(b8, sh[24 + c], res);
                     if (p.D > 2) {
-                        res = res + kSH3[0] * y * (3.0f * xx - yy) * sh[27 + c] + kSH3[1] * xy * z * sh[30 + c] +
-                              kSH3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                              kSH3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                              kSH3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] + kSH3[5] * z * (xx - yy) * sh[42 + c] +
-                              kSH3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                        res = __fmaf_rn(b9, sh[27 + c], res);
+                        res = __fmaf_rn(b10, sh[30 + c], res);
+                        res = __fmaf_rn(b11, sh[33 + c], res);
+                        res = __fmaf_rn(b12, sh[36 + c], res);
+                        res = __fmaf_rn(b13, sh[39 + c], res);
+                        res = __fmaf_rn(b14, sh[42 + c], res);
+                        res = __fmaf_rn(b15, sh[45 + c], res);
                     }
                 }
             }
-            res += 0.5f;
+            res = __fadd_rn(res, 0.5f);
             if (res < 0) clamp_bits |= (1u << c);
             rgb[c] = fmaxf(res, 0.0f);
         }

@@ -223,12 +223,12 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
             bool blend = false;
             float G = 0.f, alpha = 0.f, dx = 0.f, dy = 0.f;
             if (e < last_contributor) {
-                dx = h0.x - pxf;
-                dy = h0.y - pyf;
-                const float power = -0.5f * (h0.z * dx * dx + h1.x * dy * dy) - h0.w * dx * dy;
+                dx = __fadd_rn(h0.x, -pxf);
+                dy = __fadd_rn(h0.y, -pyf);
+                const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
                 if (!(power > 0.0f)) {
                     G = expf(power);
-                    alpha = fminf(0.99f, h1.y * G);
+                    alpha = splat_alpha(h1.y, G);
                     blend = !(alpha < 1.0f / 255.0f);
                 }
             }
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
 #pragma unroll
             for (int k = 0; k < NVP; ++k) v[k] = 0.f;
             if (blend) {
-                T = T / (1.f - alpha);
+                T = __fdiv_rn(T, __fadd_rn(1.f, -alpha));
                 const float w = alpha * T;
                 const float4* ch = reinterpret_cast<const float4*>(rb + j * RS + REC_HEAD);
                 float s = 0.f;

@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
                 bool blend = false;
                 float alpha = 0.f, test_T = 0.f;
                 if (!done) {
-                    const float dx = h0.x - pxf, dy = h0.y - pyf;
-                    const float power = -0.5f * (h0.z * dx * dx + h1.x * dy * dy) - h0.w * dx * dy;
+                    const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
+                    const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
                     if (!(power > 0.0f)) {
-                        alpha = fminf(0.99f, h1.y * expf(power));
+                        alpha = splat_alpha(h1.y, expf(power));
                         if (!(alpha < 1.0f / 255.0f)) {
-                            test_T = T * (1 - alpha);
+                            test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
                             if (test_T < 0.0001f)
                                 done = true;
                             else

@@ -128,7 +128,10 @@ def make_scene(P, W, H, F=3, seed=0, s_med: Optional[float] = None, fovx_deg=60.
 def make_all_map(scene: Scene, cam: Camera):
     """[local normal(3), 1, |n . p_cam|] as built by field_construction/gaussian_renderer/__init__.py:188-196."""
     Rw = cam.viewmatrix[:3, :3]
-    local_normal = scene.normals @ Rw
+    # normals face the camera, as GaussianModel.get_normal flips them in the reference
+    away = ((scene.means3D - cam.campos) * scene.normals).sum(-1, keepdim=True) > 0
+    normals = torch.where(away, -scene.normals, scene.normals)
+    local_normal = normals @ Rw
     pts_cam = scene.means3D @ Rw + cam.viewmatrix[3, :3]
     dist = (local_normal * pts_cam).sum(-1).abs()
     am = torch.zeros(scene.means3D.shape[0], 5, dtype=torch.float32, device=scene.means3D.device)
