@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd throughput of the rasterizer hot path on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference|reference-cpu] [--config C3]
+
+A "step" is one forward + backward of ONE 1920x1080 view of the 1M-Gaussian synthetic scene (16-d language
+feature + instance feature + normal/alpha/distance map + plane depth, SH degree 3).  With N > 1 (torchrun)
+every rank renders its own view per step (weak scaling) and the per-Gaussian parameter gradients are summed
+with one NCCL all-reduce of a flat arena inside the timed region.
+
+Printed JSON (rank 0, one line): see the task contract.  Extras: `stages_ms` (per-stage device times from the
+library's event hooks), `stats` (P_vis, R, S), `peaks` (measured FP32 / EX2 / RED.ADD rates), `ref_cuda`
+(the reference CUDA rasterizer timed in the same process when oracle/_ref is present).
+
+--impl reference       the UNMODIFIED reference CUDA rasterizer (oracle/_ref/ref_rast_f16.so, recompiled for
+                       sm_100a) driven through the same protocol — the baseline BASELINE.json's target names.
+--impl reference-cpu   the CPU restatement (oracle/) on all host threads on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(REPO, "langscene-x_b200"), REPO, os.path.join(REPO, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_case(cfg_name, device, view_yaw=0.0, seed=0):
+    from lsx_b200.synthetic import CONFIGS, make_all_map, make_camera, make_scene, make_upstream_grads
+    import harness as hz
+    c = CONFIGS[cfg_name]
+    scene = make_scene(c["P"], c["W"], c["H"], F=c["F"], seed=seed, s_med=c["s_med"]).to(device)
+    cam = make_camera(c["W"], c["H"], yaw_deg=view_yaw).to(device)
+    grads = make_upstream_grads(c["W"], c["H"], c["F"], device=device)
+    bg = torch.zeros(3, device=device)
+    am = make_all_map(scene, cam)
+    fargs = hz.native_forward_args(scene, cam, bg, c["F"], all_map=am)
+    return c, scene, cam, grads, bg, am, fargs
+
+
+def time_loop(step_fn, steps, warmup, world):
+    """W warm-ups, then exactly K steps between barrier+synchronize pairs, CUDA events, max over ranks."""
+    for _ in range(warmup):
+        step_fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def native_stepper(mod, fargs, grads, arena=None, world=1):
+    """Device-resident step: raw `_C`-level forward + backward (+ gradient all-reduce when world > 1)."""
+    import harness as hz
+    from lsx_b200.multiview import BWD_TO_GROUP
+
+    def step():
+        fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
+        bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, grads))))
+        if arena is not None:
+            arena.zero_()
+            arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items()})
+            arena.all_reduce()
+        return fwd, bwd
+    return step
+
+
+def e2e_stepper(mod, fargs, grads, cam, pinned, arena=None):
+    """End-to-end step through the operator API with HOST buffers: every step copies this view's camera and its
+    colour supervision gradient from pinned host memory, runs forward + backward, and reads a scalar back."""
+    import harness as hz
+    dev = grads["color"].device
+    d_cam = torch.empty_like(pinned["cam"], device=dev)
+    d_gcol = torch.empty_like(grads["color"])
+    fargs = list(fargs)
+    g = dict(grads)
+
+    def step():
+        d_cam.copy_(pinned["cam"], non_blocking=True)
+        d_gcol.copy_(pinned["gcol"], non_blocking=True)
+        fargs[11], fargs[12], fargs[19] = d_cam[:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
+        g["color"] = d_gcol
+        fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
+        bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, g))))
+        if arena is not None:
+            from lsx_b200.multiview import BWD_TO_GROUP
+            arena.zero_()
+            arena.accumulate({gname: bwd[k] for k, gname in BWD_TO_GROUP.items()})
+            arena.all_reduce()
+        res = torch.stack([fwd["color"].sum(), bwd["means3D"].sum()]).to("cpu", non_blocking=False)
+        return res
+    h2d = pinned["cam"].numel() * 4 + pinned["gcol"].numel() * 4
+    return step, h2d, 8
+
+
+def module_e2e_stepper(scene, cam, grads, bg, am, pinned, F, arena=None):
+    """Same as e2e_stepper but through the public nn.Module + autograd (the call a LangScene-X user makes)."""
+    from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    dev = scene.means3D.device
+    d_cam = torch.empty_like(pinned["cam"], device=dev)
+    d_gcol = torch.empty_like(grads["color"])
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    params = dict(means3D=leaf(scene.means3D), shs=leaf(scene.shs), lang=leaf(scene.language_feature),
+                  inst=leaf(scene.instance_feature), opac=leaf(scene.opacities), scales=leaf(scene.scales),
+                  rots=leaf(scene.rotations), am=leaf(am))
+    m2 = torch.zeros_like(scene.means3D, requires_grad=True)
+    m2a = torch.zeros_like(scene.means3D, requires_grad=True)
+
+    def step():
+        d_cam.copy_(pinned["cam"], non_blocking=True)
+        d_gcol.copy_(pinned["gcol"], non_blocking=True)
+        s = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
+                                          d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
+        for p in list(params.values()) + [m2, m2a]:
+            p.grad = None
+        out = GaussianRasterizer(s)(means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"],
+                                    shs=params["shs"], language_feature_precomp=params["lang"],
+                                    language_feature_instance_precomp=params["inst"], scales=params["scales"],
+                                    rotations=params["rots"], all_map=params["am"])
+        color, lf, li, _, _, amap, depth = out
+        torch.autograd.backward([color, lf, li, amap, depth],
+                                [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
+                                 grads["plane_depth"]])
+        if arena is not None:
+            arena.zero_()
+            arena.accumulate({"means3D": params["means3D"].grad, "sh": params["shs"].grad, "opacity": params["opac"].grad,
+                              "scales": params["scales"].grad, "rotations": params["rots"].grad,
+                              "language_feature": params["lang"].grad, "instance_feature": params["inst"].grad,
+                              "all_map": params["am"].grad})
+            arena.all_reduce()
+        return torch.stack([color.sum(), params["means3D"].grad.sum()]).to("cpu")
+    h2d = pinned["cam"].numel() * 4 + pinned["gcol"].numel() * 4
+    return step, h2d, 8
+
+
+def algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi):
+    """Compulsory HBM traffic per fwd+bwd iteration, SURVEY.md §8d."""
+    Ct = 3 + F + Fi + 5
+    fwd = P * (12 + 12 + 16 + 4 + 12 * M + 4 * (F + Fi + 5)) + P_vis * 75 + 8 * P + R * 12 + R * 24 * 2 + R * 8 + \
+        R * (28 + 4 * Ct) + W * H * 4 * (Ct + 1 + 2) + 4 * P * 2
+    bwd = R * (28 + 4 * Ct) + W * H * 4 * ((Ct + 1) + 5 + 2) + P_vis * (236 + 4 * (F + Fi + 5)) + \
+        P * 4 * (3 + 3 + 3 + 3 + F + Fi + 5 + 4 + 1 + 6 + 3 * M + 3 + 4)
+    return fwd, bwd
+
+
+def run_cpu_sample(threads=None):
+    """The CPU restatement on a bounded sample: the C3 generator scaled by 1/16 in pixels and Gaussians
+    (480x270, 62 500 Gaussians, same splat size in pixels => same per-pixel list statistics), fwd+bwd once."""
+    from oracle import oracle as orc
+    from lsx_b200.synthetic import make_all_map, make_camera, make_scene, make_upstream_grads
+    P, W, H, F = 62_500, 480, 270, 16
+    if threads:
+        orc.set_num_threads(threads)
+    scene, cam = make_scene(P, W, H, F=F, seed=0), make_camera(W, H)
+    am, g = make_all_map(scene, cam), make_upstream_grads(W, H, F)
+    n = lambda t: t.numpy()
+    best = 1e30
+    for _ in range(2):
+        t0 = time.perf_counter()
+        o = orc.rasterize_forward(n(scene.means3D), n(scene.opacities), n(cam.viewmatrix), n(cam.projmatrix), n(cam.campos),
+                                  W, H, cam.tanfovx, cam.tanfovy, [0, 0, 0], shs=n(scene.shs), scales=n(scene.scales),
+                                  rotations=n(scene.rotations), language_feature=n(scene.language_feature),
+                                  instance_feature=n(scene.instance_feature), all_map=n(am))
+        orc.rasterize_backward(o, n(g["color"]), n(g["language_feature"]), n(g["instance_feature"]), n(g["all_map"]),
+                               n(g["plane_depth"]))
+        best = min(best, time.perf_counter() - t0)
+    return {"value": W * H / best / 1e6, "unit": "MPix/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"oracle/lsx_oracle.c (OpenMP) fwd+bwd, best of 2, on the C3 generator scaled 1/16: {P} Gaussians, "
+                      f"{W}x{H}, F=16 (+3 instance, +5 map), R={o['num_rendered']}, {best:.2f} s/iter; "
+                      f"host has {os.cpu_count()} logical cores"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="new", choices=["new", "reference", "reference-cpu"])
+    ap.add_argument("--config", default="C3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference-cpu":
+        if rank == 0:
+            cb = run_cpu_sample()
+            print(json.dumps({"impl": "reference-cpu", "metric": METRIC, "value": cb["value"], "unit": "MPix/s",
+                              "n_gpus": 0, "steps": 1, "warmup": 1, "higher_is_better": True, "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0,
+                                      "d2h_bytes_per_step": 0}}))
+        return
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import harness as hz
+    from lsx_b200 import _lib, ops
+    from lsx_b200.multiview import GradArena
+
+    hbm_peak, peak_src, peaks_json = load_peaks()
+    # every rank renders its own view of the shared scene (yaw spread like the multi-view generator)
+    yaw = 0.0 if world == 1 else (-15.0 + 30.0 * rank / (world - 1))
+    c, scene, cam, grads, bg, am, fargs = build_case(args.config, device, view_yaw=yaw)
+    P, W, H, F = c["P"], c["W"], c["H"], c["F"]
+    M, Fi = 16, 3
+
+    if args.impl == "reference":
+        mod = hz.ref_rast_for(F)
+        if mod is None:
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/*.so not built (reference tree was not mounted at build time)"}))
+            return
+    else:
+        mod = ops
+    arena = GradArena.allocate(P, M, F, Fi, device) if world > 1 else None
+
+    # ---- device-resident timing ----------------------------------------------------------------------
+    step = native_stepper(mod, fargs, grads, arena, world)
+    fwd, bwd = step()
+    torch.cuda.synchronize()
+    R = int(fwd["num_rendered"])
+    P_vis = int((fwd["radii"] > 0).sum())
+    if args.impl == "new":
+        nbuf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H, 3 + F + Fi + 5)
+    else:
+        nbuf = hz.parse_ref_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H)
+    S = int(nbuf["n_contrib"].long().sum())
+    del nbuf, fwd, bwd
+
+    launches0 = _lib.kernel_launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total = time_loop(step, args.steps, warmup, world)
+    clocks = sampler.stop() if sampler else None
+    launches = (_lib.kernel_launch_count() - launches0) if args.impl == "new" else 0
+    ms_step = ms_total / args.steps
+    mpix = world * W * H / (ms_step * 1e-3) / 1e6
+
+    # ---- per-stage device times (separate short run so the event hooks do not touch the headline number) ----
+    stages = {}
+    if args.impl == "new":
+        _lib.profile_enable(True)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        stages = {k: v / 5 for k, v in _lib.profile_read().items() if v > 0}
+        _lib.profile_enable(False)
+
+    # ---- end-to-end through the public module API with host buffers ------------------------------------------
+    pinned = {"cam": torch.cat([cam.viewmatrix.flatten(), cam.projmatrix.flatten(), cam.campos.flatten()]).cpu().pin_memory(),
+              "gcol": grads["color"].cpu().pin_memory()}
+    if args.impl == "new":
+        estep, h2d, d2h = module_e2e_stepper(scene, cam, grads, bg, am, pinned, F, arena)
+    else:
+        estep, h2d, d2h = e2e_stepper(mod, fargs, grads, cam, pinned, arena)
+    ms_e2e = time_loop(estep, args.steps, warmup, world) / args.steps
+    e2e = {"value": world * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if args.impl == "new"
+                  else "reference _C.rasterize_gaussians/_backward (pybind)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fwd_b, bwd_b = algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi)
+    Ct = 3 + F + Fi + 5
+    out = {
+        "metric": METRIC, "value": mpix, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": args.impl,
+        "config": {"workload": f"{args.config}: {P} Gaussians, {W}x{H}, SH degree 3, F={F} language + {Fi} instance + 5 map "
+                               f"channels + plane depth, 1 view per GPU per step, fwd+bwd"
+                               + (", + NCCL all-reduce of the flat parameter-gradient arena" if world > 1 else ""),
+                   "l2": "per-step working set (~1.6 GB of inputs, records, lists, images, gradients) exceeds the 126 MB L2; no flush needed",
+                   "upstream_grads": "fixed N(0,1)/(W*H) tensors, no loss inside the timed region"},
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "stats": {"P_vis": P_vis, "R": R, "S": S, "Ct": Ct},
+        "stages_ms": stages,
+    }
+    # roofline of the dominant kernel (live stage times)
+    if stages:
+        dom = max(("render_fwd", "render_bwd"), key=lambda k: stages.get(k, 0.0))
+        rec = R * (28 + 4 * Ct)
+        kbytes = rec + W * H * 4 * (Ct + 1 + 2) if dom == "render_fwd" else rec + W * H * 4 * ((Ct + 1) + 5 + 2) + P_vis * 4 * (Ct + 8)
+        ach = kbytes / (stages[dom] * 1e-3) / 1e9
+        out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                           "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
+                           "note": "the render kernels are FP32/shuffle-issue bound, not HBM bound (see `fp32` and DESIGN.md); "
+                                   "algorithmic bytes = R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd)"}
+        it_bytes = fwd_b + bwd_b
+        out["roofline_iteration"] = {"bound": "hbm", "algorithmic_bytes": it_bytes,
+                                     "achieved": it_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": it_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak}
+        try:
+            scratch = torch.empty(64 << 20, dtype=torch.uint8, device=device)
+            res = {}
+            for kind, name in ((0, "fp32_ffma_tflops"), (1, "mufu_ex2_gops"), (2, "red_add_f32_gops")):
+                import ctypes
+                val = ctypes.c_double(0)
+                _lib.check(_lib.load().lsx_microbench(kind, scratch.data_ptr(), scratch.numel(), ctypes.byref(val),
+                                                      torch.cuda.current_stream().cuda_stream), "microbench")
+                res[name] = val.value
+            out["peaks"] = res
+            # flops model of SURVEY.md §8d with B unknown: lower bound from the per-test work only
+            out["fp32"] = {"tests_S": S, "flops_lower_bound": 14 * S + 16 * S,
+                           "achieved_tflops_lower_bound": (30 * S) / ((stages["render_fwd"] + stages["render_bwd"]) * 1e-3) / 1e12,
+                           "peak_tflops": res["fp32_ffma_tflops"]}
+        except Exception as e:  # microbench is informative only
+            out["peaks"] = {"error": str(e)[:200]}
+    if args.impl == "new" and world == 1:
+        ref = hz.ref_rast_for(F)
+        if ref is not None:
+            rstep = native_stepper(ref, fargs, grads)
+            rms = time_loop(rstep, max(5, args.steps // 2), 3, 1) / max(5, args.steps // 2)
+            out["ref_cuda"] = {"ms_per_step": rms, "value": W * H / (rms * 1e-3) / 1e6, "unit": "MPix/s",
+                               "what": "reference CUDA rasterizer (oracle/_ref/ref_rast_f16.so, sm_100a recompile), same inputs, same process",
+                               "speedup_device_resident": rms / ms_step}
+        if not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = run_cpu_sample()
+            except Exception as e:
+                out["cpu_baseline"] = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if args.impl == "reference":
+        out["cpu_baseline"] = {"value": out["value"], "unit": "MPix/s", "cores": 0, "kind": "reference",
+                               "sample": "this arm runs the reference's CUDA implementation (unmodified sources recompiled for "
+                                         "sm_100a) on the GPU — the reference has no CPU implementation of this path; the CPU "
+                                         "restatement is available with --impl reference-cpu"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

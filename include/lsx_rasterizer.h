@@ -195,6 +195,21 @@ LSX_API int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, in
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */
 LSX_API uint64_t lsx_kernel_launch_count(void);
 
+/* ---- optional per-stage device timing (events on the caller's stream; used by bench.py) ---------- */
+enum lsx_stage {
+    LSX_STAGE_PREPROCESS_FWD = 0, LSX_STAGE_DEPTH_SORT, LSX_STAGE_OFFSETS_SCAN, LSX_STAGE_EMIT, LSX_STAGE_TILE_SORT,
+    LSX_STAGE_TILE_RANGES, LSX_STAGE_RENDER_FWD, LSX_STAGE_BWD_ZERO, LSX_STAGE_RENDER_BWD, LSX_STAGE_PREPROCESS_BWD,
+    LSX_STAGE_KNN, LSX_NUM_STAGES
+};
+LSX_API void lsx_profile_enable(int enable);
+/* Synchronises the recorded events, writes the milliseconds accumulated per stage since the last read into
+ * ms_out[0..n) and returns the number of spans consumed. */
+LSX_API int lsx_profile_read(float* ms_out, int n);
+
+/* Device peaks MEASURED_PEAKS.json lacks.  kind 0: FP32 FFMA TFLOP/s, 1: MUFU.EX2 Gop/s, 2: global
+ * RED.ADD.F32 Gop/s on random addresses of a 64 MiB array.  `scratch`: device buffer of >= 64 MiB. */
+LSX_API int lsx_microbench(int kind, float* scratch, size_t scratch_bytes, double* result, void* stream);
+
 LSX_API const char* lsx_last_error(void);
 LSX_API int lsx_abi_version(void);
 

@@ -5,6 +5,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "../../include/lsx_rasterizer.h"
 #include "kernels.cuh"
@@ -21,6 +23,51 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// ---- optional per-stage device timing (bench.py's live roofline numbers) ------------------------------
+// When enabled, every stage of forward/backward is bracketed by CUDA events recorded on the caller's
+// stream; lsx_profile_read() synchronises them and returns the accumulated milliseconds per stage.
+// Disabled (the default) this costs one relaxed atomic load per stage.
+static std::atomic<int> g_profile{0};
+static std::mutex g_profile_mu;
+struct StageSpan {
+    int stage;
+    cudaEvent_t start, stop;
+};
+static std::vector<StageSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct StageTimer {
+    int stage;
+    cudaStream_t stream;
+    cudaEvent_t start = nullptr;
+    StageTimer(int st, cudaStream_t s) : stage(st), stream(s) {
+        if (g_profile.load(std::memory_order_relaxed)) {
+            std::lock_guard<std::mutex> lk(g_profile_mu);
+            start = take_event();
+            cudaEventRecord(start, stream);
+        }
+    }
+    ~StageTimer() {
+        if (start) {
+            std::lock_guard<std::mutex> lk(g_profile_mu);
+            cudaEvent_t stop = take_event();
+            cudaEventRecord(stop, stream);
+            g_spans.push_back({stage, start, stop});
+        }
+    }
+};
 
 namespace {
 
@@ -161,6 +208,24 @@ int lsx_abi_version(void) { return LSX_ABI_VERSION; }
 const char* lsx_last_error(void) { return lsx::g_error; }
 uint64_t lsx_kernel_launch_count(void) { return lsx::g_launches.load(std::memory_order_relaxed); }
 
+void lsx_profile_enable(int enable) { lsx::g_profile.store(enable ? 1 : 0, std::memory_order_relaxed); }
+
+int lsx_profile_read(float* ms_out, int n) {
+    std::lock_guard<std::mutex> lk(lsx::g_profile_mu);
+    for (int i = 0; i < n; ++i) ms_out[i] = 0.f;
+    for (auto& sp : lsx::g_spans) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(sp.stop) == cudaSuccess && cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess &&
+            sp.stage >= 0 && sp.stage < n)
+            ms_out[sp.stage] += ms;
+        lsx::g_event_pool.push_back(sp.start);
+        lsx::g_event_pool.push_back(sp.stop);
+    }
+    const int count = (int)lsx::g_spans.size();
+    lsx::g_spans.clear();
+    return count;
+}
+
 int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,
                              lsx_scratch_layout* out) {
     if (!out || P < 0 || W <= 0 || H <= 0 || R < 0 || n_blend_channels < 3 || n_blend_channels > LSX_MAX_BLEND_CHANNELS) {
@@ -261,21 +326,31 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     pp.radii = a->radii; pp.out_observe = a->out_observe; pp.depths = gm.depths; pp.depth_keys = gm.depth_keys[0];
     pp.clamped = gm.clamped; pp.means2D = gm.means2D; pp.cov3D = gm.cov3D; pp.conic_opacity = gm.conic_opacity;
     pp.rgb = gm.rgb; pp.tiles_touched = gm.tiles_touched; pp.records = gm.records;
-    int rc = launch_preprocess_fwd(pp, stream, debug);
+    int rc = 0;
+    {
+        StageTimer _t(LSX_STAGE_PREPROCESS_FWD, stream);
+        rc = launch_preprocess_fwd(pp, stream, debug);
+    }
     if (rc) return rc;
 
     // ---- depth-major presort of the Gaussians (the low-32-bit passes of the 64-bit key sort) ----
     int order_buf = 0;
-    rc = radix_sort_pairs_u32(gm.depth_keys, gm.order, P, 0, 32, /*identity_vals=*/true, gm.sort_temp, &order_buf, stream,
-                              debug);
+    {
+        StageTimer _t(LSX_STAGE_DEPTH_SORT, stream);
+        rc = radix_sort_pairs_u32(gm.depth_keys, gm.order, P, 0, 32, /*identity_vals=*/true, gm.sort_temp, &order_buf,
+                                  stream, debug);
+    }
     if (rc) return rc;
     const uint32_t* order = gm.order[order_buf];
 
     // ---- K2: duplicate offsets in depth order, total -> host ------------------------------------
-    rc = exclusive_scan_u32(gm.tiles_touched, order, gm.offsets, P, gm.total, gm.scan_temp, stream, debug);
-    if (rc) return rc;
     uint32_t R_host = 0;
-    LSX_CUDA_OK(cudaMemcpyAsync(&R_host, gm.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    {
+        StageTimer _t(LSX_STAGE_OFFSETS_SCAN, stream);
+        rc = exclusive_scan_u32(gm.tiles_touched, order, gm.offsets, P, gm.total, gm.scan_temp, stream, debug);
+        if (rc) return rc;
+        LSX_CUDA_OK(cudaMemcpyAsync(&R_host, gm.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    }
     LSX_CUDA_OK(cudaStreamSynchronize(stream));
     if (R_host > 0x7fffffffu) {
         set_error("lsx_rasterize_forward: %u duplicated splats overflow the 31-bit list index", R_host);
@@ -298,13 +373,22 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     vals[passes & 1] = bn.point_list;  // so that the sorted values end in point_list
     vals[(passes & 1) ^ 1] = bn.vals_alt;
     if (R > 0) {
-        rc = launch_emit_tile_pairs(P, order, gm.offsets, gm.means2D, a->radii, grid_x, grid_y, bn.tile_keys[0], vals[0],
-                                    stream, debug);
+        {
+            StageTimer _t(LSX_STAGE_EMIT, stream);
+            rc = launch_emit_tile_pairs(P, order, gm.offsets, gm.means2D, a->radii, grid_x, grid_y, bn.tile_keys[0],
+                                        vals[0], stream, debug);
+        }
         if (rc) return rc;
         int res = 0;
-        rc = radix_sort_pairs_u32(bn.tile_keys, vals, R, 0, tile_bits, false, bn.sort_temp, &res, stream, debug);
+        {
+            StageTimer _t(LSX_STAGE_TILE_SORT, stream);
+            rc = radix_sort_pairs_u32(bn.tile_keys, vals, R, 0, tile_bits, false, bn.sort_temp, &res, stream, debug);
+        }
         if (rc) return rc;
-        rc = launch_tile_ranges(R, bn.tile_keys[res], im.ranges, num_tiles, stream, debug);
+        {
+            StageTimer _t(LSX_STAGE_TILE_RANGES, stream);
+            rc = launch_tile_ranges(R, bn.tile_keys[res], im.ranges, num_tiles, stream, debug);
+        }
         if (rc) return rc;
     } else {
         rc = launch_tile_ranges(0, nullptr, im.ranges, num_tiles, stream, debug);
@@ -321,7 +405,10 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     rp.out_color = a->out_color; rp.out_language_feature = a->out_language_feature;
     rp.out_language_feature_instance = a->out_language_feature_instance; rp.out_observe = a->out_observe;
     rp.out_all_map = a->out_all_map; rp.out_plane_depth = a->out_plane_depth;
-    rc = launch_render_fwd(rp, stream, debug);
+    {
+        StageTimer _t(LSX_STAGE_RENDER_FWD, stream);
+        rc = launch_render_fwd(rp, stream, debug);
+    }
     if (rc) return rc;
     if (!a->render_geo) {
         LSX_CUDA_OK(cudaMemsetAsync(a->out_all_map, 0, 5 * HW * sizeof(float), stream));
@@ -369,6 +456,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), R, nullptr);
 
     const size_t p = (size_t)P;
+    StageTimer* zero_t = new StageTimer(LSX_STAGE_BWD_ZERO, stream);
     LSX_CUDA_OK(cudaMemsetAsync(a->dL_dmeans2D, 0, 3 * p * sizeof(float), stream));
     LSX_CUDA_OK(cudaMemsetAsync(a->dL_dmeans2D_abs, 0, 3 * p * sizeof(float), stream));
     LSX_CUDA_OK(cudaMemsetAsync(a->dL_dconic, 0, 4 * p * sizeof(float), stream));
@@ -379,6 +467,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
         LSX_CUDA_OK(cudaMemsetAsync(a->dL_dlanguage_feature, 0, p * F * sizeof(float), stream));
         LSX_CUDA_OK(cudaMemsetAsync(a->dL_dlanguage_feature_instance, 0, p * Fi * sizeof(float), stream));
     }
+    delete zero_t;
 
     int rc = 0;
     if (R > 0) {
@@ -396,7 +485,10 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
         rp.dL_dopacity = a->dL_dopacity; rp.dL_dcolors = a->dL_dcolors;
         rp.dL_dlanguage_feature = a->dL_dlanguage_feature;
         rp.dL_dlanguage_feature_instance = a->dL_dlanguage_feature_instance; rp.dL_dall_map = a->dL_dall_map;
-        rc = launch_render_bwd(rp, stream, debug);
+        {
+            StageTimer _t(LSX_STAGE_RENDER_BWD, stream);
+            rc = launch_render_bwd(rp, stream, debug);
+        }
         if (rc) return rc;
     }
 
@@ -410,6 +502,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     bp.dL_dmean2D = a->dL_dmeans2D; bp.dL_dconic = a->dL_dconic; bp.dL_dcolor = a->dL_dcolors;
     bp.dL_dmeans3D = a->dL_dmeans3D; bp.dL_dcov3D = a->dL_dcov3D; bp.dL_dsh = a->dL_dsh;
     bp.dL_dscales = a->dL_dscales; bp.dL_drotations = a->dL_drotations;
+    StageTimer _t(LSX_STAGE_PREPROCESS_BWD, stream);
     return launch_preprocess_bwd(bp, stream, debug);
 }
 
@@ -434,6 +527,7 @@ int lsx_knn_mean_dist2(int32_t P, const float* points, float* out, lsx_alloc_fn 
         set_error("lsx_knn_mean_dist2: scratch allocation failed");
         return -4;
     }
+    StageTimer _t(LSX_STAGE_KNN, static_cast<cudaStream_t>(stream));
     return knn_mean_dist2(P, points, out, temp, static_cast<cudaStream_t>(stream));
 }
 

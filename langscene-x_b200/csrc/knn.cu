@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_query_kernel(int P, cons
                 if (is_self && k == lane) continue;
                 const float4 c = s_pts[warp][k];
                 const float dx = c.x - q.x, dy = c.y - q.y, dz = c.z - q.z;
-                insert3(best, dx * dx + dy * dy + dz * dz);
+                // operation order of the reference's SASS: fma(dz,dz, fma(dx,dx, dy*dy))
+                insert3(best, __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy))));
             }
         }
     };

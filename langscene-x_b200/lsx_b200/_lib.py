@@ -77,6 +77,9 @@ EXPORTS = {
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
     "lsx_kernel_launch_count": (c_uint64, []),
+    "lsx_profile_enable": (None, [c_int32]),
+    "lsx_profile_read": (c_int32, [POINTER(c_float), c_int32]),
+    "lsx_microbench": (c_int32, [c_int32, c_void_p, c_size_t, POINTER(ctypes.c_double), c_void_p]),
     "lsx_last_error": (c_char_p, []),
     "lsx_abi_version": (c_int32, []),
 }
@@ -115,6 +118,21 @@ def last_error():
 def check(status, what):
     if status != 0:
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
+
+
+STAGES = ["preprocess_fwd", "depth_sort", "offsets_scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "bwd_zero",
+          "render_bwd", "preprocess_bwd", "knn"]
+
+
+def profile_enable(on=True):
+    load().lsx_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """dict stage -> milliseconds accumulated since the last read (synchronises the recorded events)."""
+    buf = (c_float * len(STAGES))()
+    load().lsx_profile_read(buf, len(STAGES))
+    return {name: float(buf[i]) for i, name in enumerate(STAGES)}
 
 
 def kernel_launch_count():

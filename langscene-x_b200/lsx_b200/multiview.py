@@ -1,0 +1,134 @@
+"""View-sharded multi-GPU optimisation support — a NEW capability, the reference is single-GPU.
+
+One process per GPU.  Every rank holds a full replica of the Gaussian parameters and renders the views
+`{v : v mod N == rank}` of a batch; per-Gaussian parameter gradients of the local views are summed into ONE
+flat fp32 arena (the layout the rasterizer's backward already produces), which is all-reduced with a single
+NCCL call over NVLink/NVSwitch.  Densification statistics keep the reference's per-view semantics
+(field_construction/scene/gaussian_model.py:720-724, field_construction/gaussian_field.py:523-524):
+sums of per-view gradient NORMS and visibility counts, max of radii.
+
+The host-side logic here is device-agnostic so it can be exercised with the gloo backend on CPU tensors.
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+# per-Gaussian parameter-gradient groups, in arena order (name, trailing shape as a function of (M, F, Fi))
+PARAM_GROUPS = ("means3D", "sh", "opacity", "scales", "rotations", "language_feature", "instance_feature", "all_map")
+
+
+def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
+    """Views rendered by `rank`: round-robin so that neighbouring (similar-cost) views spread over ranks."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of size {world_size}")
+    return list(range(rank, n_views, world_size))
+
+
+def group_widths(M: int, F: int, Fi: int) -> Dict[str, int]:
+    return {"means3D": 3, "sh": 3 * M, "opacity": 1, "scales": 3, "rotations": 4, "language_feature": F,
+            "instance_feature": Fi, "all_map": 5}
+
+
+@dataclass
+class GradArena:
+    """Flat accumulation buffer for the parameter gradients of P Gaussians."""
+    flat: torch.Tensor
+    views: Dict[str, torch.Tensor]
+
+    @staticmethod
+    def allocate(P: int, M: int, F: int, Fi: int, device) -> "GradArena":
+        widths = group_widths(M, F, Fi)
+        offs, total = {}, 0
+        for name in PARAM_GROUPS:
+            n = P * widths[name]
+            offs[name] = (total, n)
+            total += (n + 63) // 64 * 64  # 256-B aligned groups (float4 stores, NCCL-friendly)
+        flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
+        views = {name: flat[o:o + n].view(P, widths[name]) if widths[name] else flat[o:o]
+                 for name, (o, n) in offs.items()}
+        return GradArena(flat, views)
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+    def accumulate(self, grads: Dict[str, torch.Tensor]):
+        """Add one view's gradients (any tensors reshapeable to (P, width)); missing / empty groups are skipped."""
+        for name, v in self.views.items():
+            g = grads.get(name)
+            if g is None or g.numel() != v.numel() or v.numel() == 0:
+                continue
+            v.add_(g.reshape(v.shape))
+        return self
+
+    def all_reduce(self, group=None, async_op=False):
+        """Sum over ranks with ONE collective on the flat buffer."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return None
+
+
+@dataclass
+class DensifyStats:
+    """xyz_gradient_accum, xyz_gradient_accum_abs, denom (sums) and max_radii2D (max), per Gaussian."""
+    grad_accum: torch.Tensor
+    grad_accum_abs: torch.Tensor
+    denom: torch.Tensor
+    max_radii2D: torch.Tensor
+
+    @staticmethod
+    def allocate(P: int, device) -> "DensifyStats":
+        z = lambda: torch.zeros(P, dtype=torch.float32, device=device)
+        return DensifyStats(z(), z(), z(), z())
+
+    def add_view(self, means2D_grad, means2D_abs_grad, radii, out_observe=None):
+        """Per-view update, exactly the reference's: norms of the (x,y) screen gradients of visible Gaussians."""
+        visible = radii > 0
+        self.grad_accum += torch.where(visible, means2D_grad[:, :2].norm(dim=-1), torch.zeros_like(self.grad_accum))
+        self.grad_accum_abs += torch.where(visible, means2D_abs_grad[:, :2].norm(dim=-1), torch.zeros_like(self.grad_accum))
+        self.denom += visible.to(self.denom.dtype)
+        mask = visible if out_observe is None else (visible & (out_observe > 0))
+        self.max_radii2D = torch.where(mask, torch.maximum(self.max_radii2D, radii.to(self.max_radii2D.dtype)),
+                                       self.max_radii2D)
+
+    def all_reduce(self, group=None):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        packed = torch.stack([self.grad_accum, self.grad_accum_abs, self.denom])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        self.grad_accum, self.grad_accum_abs, self.denom = packed[0], packed[1], packed[2]
+        dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+BWD_TO_GROUP = {"means3D": "means3D", "sh": "sh", "opacity": "opacity", "scales": "scales", "rotations": "rotations",
+                "language_feature": "language_feature", "instance_feature": "instance_feature", "all_map": "all_map"}
+
+
+def accumulate_views(render_view, view_ids: Sequence[int], arena: GradArena, stats: DensifyStats = None
+                     ) -> Tuple[GradArena, int]:
+    """Run `render_view(v) -> (fwd dict, bwd dict)` for the local views and sum their gradients into the arena.
+
+    `bwd` uses the names of the native backward tuple (means2D, means2D_abs, colors, language_feature,
+    instance_feature, opacity, means3D, cov3D, sh, scales, rotations, all_map)."""
+    n = 0
+    for v in view_ids:
+        fwd, bwd = render_view(v)
+        arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items() if k in bwd})
+        if stats is not None:
+            stats.add_view(bwd["means2D"], bwd["means2D_abs"], fwd["radii"], fwd.get("out_observe"))
+        n += 1
+    return arena, n
+
+
+def multiview_step(render_view, n_views: int, arena: GradArena, stats: DensifyStats = None, group=None):
+    """One optimisation step's gradient: local views -> arena -> one all-reduce.  Returns #local views."""
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    arena.zero_()
+    _, n_local = accumulate_views(render_view, shard_views(n_views, world, rank), arena, stats)
+    arena.all_reduce(group)
+    if stats is not None:
+        stats.all_reduce(group)
+    return n_local
