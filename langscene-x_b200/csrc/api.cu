@@ -259,8 +259,8 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
                   LSX_MAX_BLEND_CHANNELS);
         return -1;
     }
-    if (!a->out_color || !a->radii || !a->out_observe || !a->out_all_map || !a->out_plane_depth || !a->background ||
-        !a->viewmatrix || !a->projmatrix || !a->campos) {
+    if (!a->out_color || !a->out_all_map || !a->out_plane_depth ||
+        (P > 0 && (!a->radii || !a->out_observe || !a->background || !a->viewmatrix || !a->projmatrix || !a->campos))) {
         set_error("lsx_rasterize_forward: a required pointer is null");
         return -1;
     }
