@@ -198,7 +198,7 @@ LSX_API uint64_t lsx_kernel_launch_count(void);
 /* ---- optional per-stage device timing (events on the caller's stream; used by bench.py) ---------- */
 enum lsx_stage {
     LSX_STAGE_PREPROCESS_FWD = 0, LSX_STAGE_DEPTH_SORT, LSX_STAGE_OFFSETS_SCAN, LSX_STAGE_EMIT, LSX_STAGE_TILE_SORT,
-    LSX_STAGE_TILE_RANGES, LSX_STAGE_RENDER_FWD, LSX_STAGE_BWD_ZERO, LSX_STAGE_RENDER_BWD, LSX_STAGE_PREPROCESS_BWD,
+    LSX_STAGE_TILE_RANGES, LSX_STAGE_FOOTPRINT_MASKS, LSX_STAGE_RENDER_FWD, LSX_STAGE_BWD_ZERO, LSX_STAGE_RENDER_BWD, LSX_STAGE_PREPROCESS_BWD,
     LSX_STAGE_KNN, LSX_NUM_STAGES
 };
 LSX_API void lsx_profile_enable(int enable);

@@ -97,6 +97,7 @@ struct GeomScratch {
     float* rgb;
     uint32_t* tiles_touched;
     float* records;
+    float* grad_records;  // packed per-Gaussian gradient accumulators for the backward pass (zeroed there)
     // forward-only temporaries
     uint32_t* depth_keys[2];
     uint32_t* order[2];  // Gaussian indices, ping-pong; the depth-sorted order ends in one of them
@@ -121,6 +122,7 @@ GeomScratch carve_geom(char* base, int P, int rec_stride) {
     g.tiles_touched = c.take<uint32_t>(p, &g.lay.tiles_touched);
     g.records = c.take<float>(p * rec_stride, &g.lay.records);
     g.lay.record_stride = rec_stride;
+    g.grad_records = c.take<float>(p * (size_t)(rec_stride - REC_HEAD + 8));  // >= round_up4(channels) + 8 per Gaussian
     g.depth_keys[0] = c.take<uint32_t>(p);
     g.depth_keys[1] = c.take<uint32_t>(p);
     g.order[0] = c.take<uint32_t>(p);
@@ -162,6 +164,7 @@ ImageScratch carve_image(char* base, int W, int H, lsx_scratch_layout* lay) {
 
 struct BinningScratch {
     uint32_t* point_list;
+    uint8_t* masks;  // sub-tile footprint mask per list entry (cull.cu), kept for the backward pass
     uint32_t* vals_alt;
     uint32_t* tile_keys[2];
     void* sort_temp;
@@ -174,6 +177,7 @@ BinningScratch carve_binning(char* base, int R, lsx_scratch_layout* lay) {
     const size_t r = (size_t)(R > 0 ? R : 0);
     size_t o0;
     s.point_list = c.take<uint32_t>(r, &o0);
+    s.masks = c.take<uint8_t>(r);
     s.vals_alt = c.take<uint32_t>(r);
     s.tile_keys[0] = c.take<uint32_t>(r);
     s.tile_keys[1] = c.take<uint32_t>(r);
@@ -390,6 +394,11 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
             rc = launch_tile_ranges(R, bn.tile_keys[res], im.ranges, num_tiles, stream, debug);
         }
         if (rc) return rc;
+        {
+            StageTimer _t(LSX_STAGE_FOOTPRINT_MASKS, stream);
+            rc = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, stream, debug);
+        }
+        if (rc) return rc;
     } else {
         rc = launch_tile_ranges(0, nullptr, im.ranges, num_tiles, stream, debug);
         if (rc) return rc;
@@ -400,7 +409,8 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
     rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
     rp.n_channels = nch; rp.rec_stride = rs;
-    rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.records = gm.records; rp.bg = a->background;
+    rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
+    rp.bg = a->background;
     rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
     rp.out_color = a->out_color; rp.out_language_feature = a->out_language_feature;
     rp.out_language_feature_instance = a->out_language_feature_instance; rp.out_observe = a->out_observe;
@@ -455,19 +465,11 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     ImageScratch im = carve_image(const_cast<char*>(a->image_buffer), W, H, nullptr);
     BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), R, nullptr);
 
-    const size_t p = (size_t)P;
-    StageTimer* zero_t = new StageTimer(LSX_STAGE_BWD_ZERO, stream);
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dmeans2D, 0, 3 * p * sizeof(float), stream));
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dmeans2D_abs, 0, 3 * p * sizeof(float), stream));
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dconic, 0, 4 * p * sizeof(float), stream));
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dopacity, 0, p * sizeof(float), stream));
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dcolors, 0, 3 * p * sizeof(float), stream));
-    LSX_CUDA_OK(cudaMemsetAsync(a->dL_dall_map, 0, 5 * p * sizeof(float), stream));
-    if (a->include_feature) {
-        LSX_CUDA_OK(cudaMemsetAsync(a->dL_dlanguage_feature, 0, p * F * sizeof(float), stream));
-        LSX_CUDA_OK(cudaMemsetAsync(a->dL_dlanguage_feature_instance, 0, p * Fi * sizeof(float), stream));
+    const int gs = round_up4(nch) + 8;  // floats per packed gradient record
+    {
+        StageTimer _t(LSX_STAGE_BWD_ZERO, stream);
+        LSX_CUDA_OK(cudaMemsetAsync(gm.grad_records, 0, (size_t)P * gs * sizeof(float), stream));
     }
-    delete zero_t;
 
     int rc = 0;
     if (R > 0) {
@@ -475,16 +477,14 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
         rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
         rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
         rp.n_channels = nch; rp.rec_stride = rs;
-        rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.records = gm.records; rp.bg = a->background;
+        rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
+        rp.bg = a->background;
         rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
         rp.dL_dout_color = a->dL_dout_color; rp.dL_dout_language_feature = a->dL_dout_language_feature;
         rp.dL_dout_language_feature_instance = a->dL_dout_language_feature_instance;
         rp.dL_dout_all_map = a->dL_dout_all_map; rp.dL_dout_plane_depth = a->dL_dout_plane_depth;
         rp.all_map_pixels = a->out_all_map;
-        rp.dL_dmean2D = a->dL_dmeans2D; rp.dL_dmean2D_abs = a->dL_dmeans2D_abs; rp.dL_dconic = a->dL_dconic;
-        rp.dL_dopacity = a->dL_dopacity; rp.dL_dcolors = a->dL_dcolors;
-        rp.dL_dlanguage_feature = a->dL_dlanguage_feature;
-        rp.dL_dlanguage_feature_instance = a->dL_dlanguage_feature_instance; rp.dL_dall_map = a->dL_dall_map;
+        rp.grad_records = gm.grad_records;
         {
             StageTimer _t(LSX_STAGE_RENDER_BWD, stream);
             rc = launch_render_bwd(rp, stream, debug);
@@ -499,7 +499,12 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     bp.means3D = a->means3D; bp.radii = a->radii; bp.shs = a->shs; bp.clamped = gm.clamped;
     bp.scales = a->scales; bp.rotations = a->rotations; bp.cov3D = gm.cov3D; bp.cov3D_precomp = a->cov3D_precomp;
     bp.view = a->viewmatrix; bp.proj = a->projmatrix; bp.campos = a->campos;
-    bp.dL_dmean2D = a->dL_dmeans2D; bp.dL_dconic = a->dL_dconic; bp.dL_dcolor = a->dL_dcolors;
+    bp.grad_records = gm.grad_records; bp.grad_stride = gs; bp.n_channels_pad = round_up4(nch);
+    bp.F = F; bp.Fi = Fi; bp.include_feature = a->include_feature; bp.render_geo = a->render_geo;
+    bp.dL_dmean2D = a->dL_dmeans2D; bp.dL_dmean2D_abs = a->dL_dmeans2D_abs; bp.dL_dconic = a->dL_dconic;
+    bp.dL_dopacity = a->dL_dopacity; bp.dL_dcolor = a->dL_dcolors;
+    bp.dL_dlanguage_feature = a->dL_dlanguage_feature;
+    bp.dL_dlanguage_feature_instance = a->dL_dlanguage_feature_instance; bp.dL_dall_map = a->dL_dall_map;
     bp.dL_dmeans3D = a->dL_dmeans3D; bp.dL_dcov3D = a->dL_dcov3D; bp.dL_dsh = a->dL_dsh;
     bp.dL_dscales = a->dL_dscales; bp.dL_drotations = a->dL_drotations;
     StageTimer _t(LSX_STAGE_PREPROCESS_BWD, stream);

@@ -53,9 +53,20 @@ struct PreprocessBwdParams {
     const float* view;
     const float* proj;
     const float* campos;
-    const float* dL_dmean2D;  // (P,3)
-    const float* dL_dconic;   // (P,4)
-    const float* dL_dcolor;   // (P,3)
+    // packed gradient records written by the tile backward pass (see RenderParams::grad_records)
+    const float* grad_records;
+    int grad_stride;  // floats per record
+    int n_channels_pad;  // round_up4(blended channels) = offset of the geometry terms inside a record
+    int F, Fi, include_feature, render_geo;
+    // per-tensor outputs in the reference's layouts (every row written; zeros for culled splats)
+    float* dL_dmean2D;      // (P,3)
+    float* dL_dmean2D_abs;  // (P,3)
+    float* dL_dconic;       // (P,4) as {x,y,0,w}
+    float* dL_dopacity;     // (P)
+    float* dL_dcolor;       // (P,3)
+    float* dL_dlanguage_feature;
+    float* dL_dlanguage_feature_instance;
+    float* dL_dall_map;     // (P,5)
     float* dL_dmeans3D;
     float* dL_dcov3D;
     float* dL_dsh;
@@ -89,6 +100,8 @@ int launch_emit_tile_pairs(int P, const uint32_t* sorted_idx, const uint32_t* of
                            cudaStream_t stream, bool debug);
 int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, int num_tiles, cudaStream_t stream,
                        bool debug);
+int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,
+                           int rec_stride, uint32_t grid_x, uint8_t* masks, cudaStream_t stream, bool debug);
 int launch_debug_keys(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* depths,
                       uint64_t* keys_out, cudaStream_t stream);
 
@@ -103,6 +116,7 @@ struct RenderParams {
     int rec_stride;
     const uint2* ranges;
     const uint32_t* point_list;
+    const uint8_t* masks;  // per list entry: bit w set iff the splat may blend inside block w of its tile (cull.cu)
     const float* records;
     const float* bg;
     // forward outputs / backward inputs
@@ -121,14 +135,9 @@ struct RenderParams {
     const float* dL_dout_all_map;
     const float* dL_dout_plane_depth;
     const float* all_map_pixels;
-    float* dL_dmean2D;      // (P,3)
-    float* dL_dmean2D_abs;  // (P,3)
-    float* dL_dconic;       // (P,4)
-    float* dL_dopacity;     // (P)
-    float* dL_dcolors;      // (P,3)
-    float* dL_dlanguage_feature;
-    float* dL_dlanguage_feature_instance;
-    float* dL_dall_map;     // (P,5)
+    // packed per-Gaussian gradient accumulators, stride round_up4(n_channels) + 8 floats, zero on entry:
+    // [channels in record order | mean2D.x, mean2D.y, |mean2D|.x, |mean2D|.y, conic.x, conic.y, conic.w, opacity]
+    float* grad_records;
 };
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream, bool debug);

@@ -272,6 +272,32 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwd
 // ------------------------------------------------------------------------------------------------
 // backward (K8 + K9 fused): dL/dconic, dL/dmean2D, dL/dcolor  ->  dL/d{mean3D, cov3D, sh, scale, rot}
 // ------------------------------------------------------------------------------------------------
+// Unpack one packed gradient record (render_bwd.cu) into the reference's per-tensor layouts; rec == nullptr
+// writes zeros (culled splat).  Record: [rgb(3) | language(F) | instance(Fi) | all_map(5) | pad | 8 geometry terms].
+__device__ __forceinline__ void write_screen_grads(const PreprocessBwdParams& p, const int idx, const float* __restrict__ rec) {
+    const float* geo = rec ? rec + p.n_channels_pad : nullptr;
+    auto at = [&](const float* base, int i) { return base ? base[i] : 0.f; };
+    p.dL_dmean2D[3 * idx + 0] = at(geo, 0);
+    p.dL_dmean2D[3 * idx + 1] = at(geo, 1);
+    p.dL_dmean2D[3 * idx + 2] = 0.f;
+    p.dL_dmean2D_abs[3 * idx + 0] = at(geo, 2);
+    p.dL_dmean2D_abs[3 * idx + 1] = at(geo, 3);
+    p.dL_dmean2D_abs[3 * idx + 2] = 0.f;
+    reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(at(geo, 4), at(geo, 5), 0.f, at(geo, 6));
+    p.dL_dopacity[idx] = at(geo, 7);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) p.dL_dcolor[3 * idx + k] = at(rec, k);
+    int c = 3;
+    if (p.include_feature) {
+        for (int k = 0; k < p.F; ++k) p.dL_dlanguage_feature[(size_t)idx * p.F + k] = at(rec, c + k);
+        c += p.F;
+        for (int k = 0; k < p.Fi; ++k) p.dL_dlanguage_feature_instance[(size_t)idx * p.Fi + k] = at(rec, c + k);
+        c += p.Fi;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) p.dL_dall_map[5 * idx + k] = p.render_geo ? at(rec, c + k) : 0.f;
+}
+
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwdParams p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
@@ -281,6 +307,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
 
     if (!(p.radii[idx] > 0)) {
         // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
+        write_screen_grads(p, idx, nullptr);
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
 #pragma unroll
@@ -293,6 +320,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
         return;
     }
 
+    const float* grec = p.grad_records + (size_t)idx * p.grad_stride;
+    write_screen_grads(p, idx, grec);
+    const float* ggeo = grec + p.n_channels_pad;  // mean2D.x, mean2D.y, |.|x, |.|y, conic.x, conic.y, conic.w, opacity
+
     const float3 mean = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
     const float* cov6 = (p.cov3D_precomp ? p.cov3D_precomp : p.cov3D) + 6 * (size_t)idx;
     float c6[6];
@@ -300,7 +331,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     for (int i = 0; i < 6; ++i) c6[i] = cov6[i];
 
     // ---- part 1: conic gradient through the 2D covariance (backward.cu:144-274) -----------------
-    const float3 g_conic = make_float3(p.dL_dconic[4 * idx], p.dL_dconic[4 * idx + 1], p.dL_dconic[4 * idx + 3]);
+    const float3 g_conic = make_float3(ggeo[4], ggeo[5], ggeo[6]);
     Cov2DFrame fr;
     ewa_frame(mean, p.focal_x, p.focal_y, p.tan_fovx, p.tan_fovy, c6, p.view, fr);
     const Mat3& T = fr.T;
@@ -380,7 +411,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
         const float mw = 1.0f / (mh.w + 0.0000001f);
         const float mul1 = (pr[0] * mean.x + pr[4] * mean.y + pr[8] * mean.z + pr[12]) * mw * mw;
         const float mul2 = (pr[1] * mean.x + pr[5] * mean.y + pr[9] * mean.z + pr[13]) * mw * mw;
-        const float gx = p.dL_dmean2D[3 * idx], gy = p.dL_dmean2D[3 * idx + 1];
+        const float gx = ggeo[0], gy = ggeo[1];
         float3 d;
         d.x = (pr[0] * mw - pr[3] * mul1) * gx + (pr[1] * mw - pr[3] * mul2) * gy;
         d.y = (pr[4] * mw - pr[7] * mul1) * gx + (pr[5] * mw - pr[7] * mul2) * gy;
@@ -399,7 +430,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
         const unsigned cl = p.clamped[idx];
         float gc[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) gc[k] = p.dL_dcolor[3 * idx + k] * (((cl >> k) & 1u) ? 0.f : 1.f);
+        for (int k = 0; k < 3; ++k) gc[k] = grec[k] * (((cl >> k) & 1u) ? 0.f : 1.f);
 
         // basis values (the derivative of RGB w.r.t. each coefficient) and d(RGB)/d(dir)
         float basis[16];

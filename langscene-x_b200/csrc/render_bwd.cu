@@ -13,14 +13,20 @@
 //   * the per-channel "accumulated colour behind" recurrence is linear, so its dot product with the
 //     pixel's upstream gradient is carried as ONE scalar:  A <- a_prev * s_prev + (1 - a_prev) * A  with
 //     s = <feat[g], dL/dpix>.  That removes 2*Ct registers and ~3*Ct flops per blend compared with the
-//     per-channel form, and leaves the pixel's upstream gradient vector as the only wide state.
-//   * all 32 lanes of a warp walk the list in lock-step, so the Ct+8 per-lane contributions of one
-//     Gaussian are summed ACROSS the warp before touching memory: a transposing butterfly (each step
-//     exchanges half of the remaining values) reduces N values in N-1 shuffles and leaves value k in
-//     lane k, which then issues a single RED.ADD.F32 — <= Ct+8 atomics per (warp, Gaussian) instead of
-//     32*(Ct+8), i.e. up to 32x fewer L2 atomics than the reference;
+//     per-channel form.
+//   * warp w owns the 8x4 pixel block w of the tile and visits only the list entries whose footprint-mask
+//     bit is set (cull.cu), back to front.
+//   * the channel gradients of one entry, dL/dfeat[c] = sum_pix (alpha T)_pix * dL/dpix[c], are an outer
+//     product over the warp's 32 pixels.  Each lane keeps TWO views of the block's upstream gradient in
+//     registers: its own pixel's channel vector (for s) and, transposed, channel `lane` of all 32 pixels.
+//     Per entry the 32 weights alpha*T are exchanged through 128 B of shared memory and lane c evaluates
+//     its channel's sum with 8 broadcast LDS.128 + 32 FFMA — no shuffles, no selects — then issues ONE
+//     RED.ADD.F32 into the packed per-Gaussian gradient record (the Ct lanes hit consecutive addresses).
+//     Only the 8 geometry terms (mean2D, |mean2D|, conic, opacity) go through a transposing butterfly.
+//     The reference issues Ct + 8 global atomics per (pixel, Gaussian); this kernel issues Ct + 8 per
+//     (32-pixel block, Gaussian), all into one contiguous 144-B record.
 //   * CTA-level skip of the list tail beyond the tile's deepest contributor, TMA-staged records
-//     (tile_stage.cuh), warp-ballot skip of Gaussians no lane blends.
+//     (tile_stage.cuh), warp-ballot skip of entries no lane blends.
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
@@ -51,65 +57,22 @@ struct WarpTransposeReduce {
     }
 };
 
-template <int N>
-struct Log2 {
-    static constexpr int value = 1 + Log2<N / 2>::value;
-};
-template <>
-struct Log2<1> {
-    static constexpr int value = 0;
-};
-
-struct LaneTarget {  // where a lane's reduced value goes: base + id*stride
-    float* base;
-    int stride;
-};
-
-// slot s of the per-Gaussian value vector: [0,CT4) blended channels, [CT4, CT4+8) geometry terms
-template <int CT4>
-__device__ __forceinline__ LaneTarget slot_target(const RenderParams& p, int s) {
-    LaneTarget t{nullptr, 0};
-    if (s < 0) return t;
-    if (s < CT4) {
-        int c = s;
-        if (c < 3) return LaneTarget{p.dL_dcolors + c, 3};
-        c -= 3;
-        if (p.include_feature) {
-            if (c < p.F) return LaneTarget{p.dL_dlanguage_feature + c, p.F};
-            c -= p.F;
-            if (c < p.Fi) return LaneTarget{p.dL_dlanguage_feature_instance + c, p.Fi};
-            c -= p.Fi;
-        }
-        if (p.render_geo && c < 5) return LaneTarget{p.dL_dall_map + c, 5};
-        return t;
-    }
-    switch (s - CT4) {
-        case 0: return LaneTarget{p.dL_dmean2D + 0, 3};
-        case 1: return LaneTarget{p.dL_dmean2D + 1, 3};
-        case 2: return LaneTarget{p.dL_dmean2D_abs + 0, 3};
-        case 3: return LaneTarget{p.dL_dmean2D_abs + 1, 3};
-        case 4: return LaneTarget{p.dL_dconic + 0, 4};
-        case 5: return LaneTarget{p.dL_dconic + 1, 4};
-        case 6: return LaneTarget{p.dL_dconic + 3, 4};
-        case 7: return LaneTarget{p.dL_dopacity, 1};
-        default: return t;
-    }
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 template <int CT4>
 __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    constexpr int NV = CT4 + 8;                          // values reduced per Gaussian
-    constexpr int N1 = NV <= 16 ? 16 : 32;               // first butterfly group (zero padded)
-    constexpr int REM = NV > 32 ? NV - 32 : 0;
-    constexpr int N2 = REM == 0 ? 0 : (REM <= 4 ? 4 : (REM <= 8 ? 8 : 16));
-    constexpr int NVP = N1 + N2;
+    constexpr int GS = CT4 + 8;                // floats per packed gradient record
+    constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
+    constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
+    using Stage = TileStage<RS>;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_tile_max;
-    TileStage<RS> stage;
+    __shared__ __align__(16) float s_w[TILE_PIXELS / 32][2][32];  // per-warp weight exchange, double buffered
     if (threadIdx.x == 0) s_tile_max = 0;
-    stage.init(smem_raw);  // contains a __syncthreads
 
     const int tile = blockIdx.x;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -176,113 +139,136 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
         }
     }
 
-    // deepest contributor of the tile: list entries at or beyond it are never blended by any pixel
+    // ---- transposed view: gT[ps][q] = upstream gradient of channel (32 ps + lane) at pixel q of this block ----
+    float gT[NPASS][32];
     {
-        const int wmax = __reduce_max_sync(kFull, last_contributor);
-        if (lane == 0 && wmax > 0) atomicMax(&s_tile_max, wmax);
+        float* ts = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 32 * TS;  // aliases the stage buffers (not yet live)
+#pragma unroll
+        for (int c = 0; c < CT4; ++c) ts[lane * TS + c] = g[c];
+        __syncwarp();
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) {
+            const int c = ps * 32 + (int)lane;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) gT[ps][q] = (c < CT4) ? ts[q * TS + c] : 0.f;
+        }
     }
-    __syncthreads();
+
+    // deepest contributor of the tile: list entries at or beyond it are never blended by any pixel
+    const int warp_max = __reduce_max_sync(kFull, last_contributor);
+    if (lane == 0 && warp_max > 0) atomicMax(&s_tile_max, warp_max);
+    __syncthreads();  // also: every warp is done with the transposition scratch
+    Stage stage;
+    stage.init(smem_raw);  // contains a __syncthreads
     const int n_eff = min(s_tile_max, n);
     const int nbatch = (n_eff + STAGE_BATCH - 1) / STAGE_BATCH;
 
-    // per-lane atomic targets after the butterfly
-    const LaneTarget tgt1 = slot_target<CT4>(p, (int)(lane >> (5 - Log2<N1>::value)));
-    const bool own1 = (lane & ((1u << (5 - Log2<N1>::value)) - 1u)) == 0 && tgt1.base != nullptr;
-    LaneTarget tgt2{nullptr, 0};
-    bool own2 = false;
-    if constexpr (N2 > 0) {
-        const int s2 = (int)(lane >> (5 - Log2<(N2 > 0 ? N2 : 1)>::value));
-        tgt2 = slot_target<CT4>(p, s2 < REM ? 32 + s2 : -1);
-        own2 = (lane & ((1u << (5 - Log2<(N2 > 0 ? N2 : 1)>::value)) - 1u)) == 0 && tgt2.base != nullptr;
-    }
-
-    float A = 0.f;           // <accumulated colour behind, upstream gradient>
+    float A = 0.f;  // <accumulated colour behind, upstream gradient>
     float last_alpha = 0.f;
     float last_s = 0.f;
     const float ddelx_dx = 0.5 * p.W;
     const float ddely_dy = 0.5 * p.H;
+    const uint32_t w_addr = smem_u32(&s_w[warp][0][0]);
+    unsigned parity = 0;
 
     auto entry_of = [&](int b) -> long long {
         const int e = n_eff - 1 - (b * STAGE_BATCH + (int)threadIdx.x);
         return e >= 0 ? (long long)range.x + e : -1;
     };
 
-    if (nbatch > 0) stage.issue(0, entry_of(0), p.point_list, p.records);
+    if (nbatch > 0) stage.issue(0, entry_of(0), p.point_list, p.masks, p.records);
     for (int b = 0; b < nbatch; ++b) {
-        if (b + 1 < nbatch) stage.issue(b + 1, entry_of(b + 1), p.point_list, p.records);
+        if (b + 1 < nbatch) stage.issue(b + 1, entry_of(b + 1), p.point_list, p.masks, p.records);
         stage.wait(b);
-        const float* rb = stage.rec_buf(b);
-        const int* ib = stage.id_buf(b);
+        const uint32_t rec0 = stage.rec_addr(b), ids0 = stage.ids_addr(b), msk0 = stage.mask_addr(b);
         const int cnt = min(STAGE_BATCH, n_eff - b * STAGE_BATCH);
         const int e0 = n_eff - 1 - b * STAGE_BATCH;  // list index of slot 0
 
-        for (int j = 0; j < cnt; ++j) {
-            const int e = e0 - j;
-            const float4 h0 = *reinterpret_cast<const float4*>(rb + j * RS);
-            const float2 h1 = *reinterpret_cast<const float2*>(rb + j * RS + 4);
-            bool blend = false;
-            float G = 0.f, alpha = 0.f, dx = 0.f, dy = 0.f;
-            if (e < last_contributor) {
-                dx = __fadd_rn(h0.x, -pxf);
-                dy = __fadd_rn(h0.y, -pyf);
+        for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
+            // slots of this chunk that can touch this warp's block and lie below its deepest contributor
+            const int slot = chunk * 32 + (int)lane;
+            unsigned bits = __ballot_sync(kFull, ((lds8u(msk0 + slot) >> warp) & 1u) && (e0 - slot < warp_max));
+            while (bits) {
+                const int j = chunk * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int e = e0 - j;
+                const uint32_t ra = rec0 + (uint32_t)j * Stage::kRecBytes;
+                const float4 h0 = lds128(ra);
+                const float2 h1 = lds64(ra + 16);
+                const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
                 const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-                if (!(power > 0.0f)) {
-                    G = expf(power);
-                    alpha = splat_alpha(h1.y, G);
-                    blend = !(alpha < 1.0f / 255.0f);
-                }
-            }
-            if (__ballot_sync(kFull, blend) == 0) continue;
+                const float G = expf(power);
+                const float alpha = splat_alpha(h1.y, G);
+                const bool blend = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                if (__ballot_sync(kFull, blend) == 0) continue;
 
-            float v[NVP];
+                float w = 0.f;
+                float v[8];
 #pragma unroll
-            for (int k = 0; k < NVP; ++k) v[k] = 0.f;
-            if (blend) {
-                T = __fdiv_rn(T, __fadd_rn(1.f, -alpha));
-                const float w = alpha * T;
-                const float4* ch = reinterpret_cast<const float4*>(rb + j * RS + REC_HEAD);
-                float s = 0.f;
+                for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                if (blend) {
+                    T = __fdiv_rn(T, __fadd_rn(1.f, -alpha));
+                    w = alpha * T;
+                    float s = 0.f;
 #pragma unroll
-                for (int q = 0; q < CT4 / 4; ++q) {
-                    const float4 f = ch[q];
-                    s += f.x * g[4 * q + 0];
-                    s += f.y * g[4 * q + 1];
-                    s += f.z * g[4 * q + 2];
-                    s += f.w * g[4 * q + 3];
-                    v[4 * q + 0] = w * g[4 * q + 0];
-                    v[4 * q + 1] = w * g[4 * q + 1];
-                    v[4 * q + 2] = w * g[4 * q + 2];
-                    v[4 * q + 3] = w * g[4 * q + 3];
+                    for (int q = 0; q < CT4 / 4; ++q) {
+                        const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
+                        s += f.x * g[4 * q + 0];
+                        s += f.y * g[4 * q + 1];
+                        s += f.z * g[4 * q + 2];
+                        s += f.w * g[4 * q + 3];
+                    }
+                    A = last_alpha * last_s + (1.f - last_alpha) * A;
+                    last_s = s;
+                    float dL_dalpha = (s - A) * T;
+                    last_alpha = alpha;
+                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+
+                    const float dL_dG = h1.y * dL_dalpha;
+                    const float gdx = G * dx;
+                    const float gdy = G * dy;
+                    const float dG_ddelx = -gdx * h0.z - gdy * h0.w;
+                    const float dG_ddely = -gdy * h1.x - gdx * h0.w;
+                    const float mx = dL_dG * dG_ddelx * ddelx_dx;
+                    const float my = dL_dG * dG_ddely * ddely_dy;
+                    v[0] = mx;
+                    v[1] = my;
+                    v[2] = fabsf(mx);
+                    v[3] = fabsf(my);
+                    v[4] = -0.5f * gdx * dx * dL_dG;
+                    v[5] = -0.5f * gdx * dy * dL_dG;
+                    v[6] = -0.5f * gdy * dy * dL_dG;
+                    v[7] = G * dL_dalpha;
                 }
-                A = last_alpha * last_s + (1.f - last_alpha) * A;
-                last_s = s;
-                float dL_dalpha = (s - A) * T;
-                last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
 
-                const float dL_dG = h1.y * dL_dalpha;
-                const float gdx = G * dx;
-                const float gdy = G * dy;
-                const float dG_ddelx = -gdx * h0.z - gdy * h0.w;
-                const float dG_ddely = -gdy * h1.x - gdx * h0.w;
-                const float mx = dL_dG * dG_ddelx * ddelx_dx;
-                const float my = dL_dG * dG_ddely * ddely_dy;
-                v[CT4 + 0] = mx;
-                v[CT4 + 1] = my;
-                v[CT4 + 2] = fabsf(mx);
-                v[CT4 + 3] = fabsf(my);
-                v[CT4 + 4] = -0.5f * gdx * dx * dL_dG;
-                v[CT4 + 5] = -0.5f * gdx * dy * dL_dG;
-                v[CT4 + 6] = -0.5f * gdy * dy * dL_dG;
-                v[CT4 + 7] = G * dL_dalpha;
-            }
-
-            const int id = ib[j];
-            WarpTransposeReduce<N1, 16>::run(v, lane);
-            if (own1 && v[0] != 0.f) atomicAdd(tgt1.base + (size_t)id * tgt1.stride, v[0]);
-            if constexpr (N2 > 0) {
-                WarpTransposeReduce<N2, 16>::run(v + N1, lane);
-                if (own2 && v[N1] != 0.f) atomicAdd(tgt2.base + (size_t)id * tgt2.stride, v[N1]);
+                // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
+                const uint32_t wa = w_addr + parity * 128u;
+                parity ^= 1u;
+                sts32(wa + lane * 4u, w);
+                __syncwarp();
+                float cg[NPASS];
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) cg[ps] = 0.f;
+#pragma unroll
+                for (int q4 = 0; q4 < 8; ++q4) {
+                    const float4 wq = lds128(wa + q4 * 16);
+#pragma unroll
+                    for (int ps = 0; ps < NPASS; ++ps) {
+                        cg[ps] += wq.x * gT[ps][4 * q4 + 0];
+                        cg[ps] += wq.y * gT[ps][4 * q4 + 1];
+                        cg[ps] += wq.z * gT[ps][4 * q4 + 2];
+                        cg[ps] += wq.w * gT[ps][4 * q4 + 3];
+                    }
+                }
+                float* grec = p.grad_records + (size_t)lds32i(ids0 + j * 4) * GS;
+#pragma unroll
+                for (int ps = 0; ps < NPASS; ++ps) {
+                    const int c = ps * 32 + (int)lane;
+                    if (c < p.n_channels && cg[ps] != 0.f) atomicAdd(grec + c, cg[ps]);
+                }
+                // ---- geometry terms: 8 values -> lanes 0,4,...,28 ----
+                WarpTransposeReduce<8, 16>::run(v, lane);
+                if ((lane & 3u) == 0u && v[0] != 0.f) atomicAdd(grec + CT4 + (lane >> 2), v[0]);
             }
         }
         __syncthreads();  // frees buffer (b & 1) for batch b + 2

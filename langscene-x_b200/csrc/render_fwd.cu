@@ -8,14 +8,17 @@
 //   plane_depth = A4 / -(A0*ray.x + A1*ray.y + A2 + 1e-8) evaluated in double.
 //
 // B200 design
-//   * one CTA per 16x16 tile, one thread per pixel; a warp owns a compact 8x4 pixel block (32-B row
-//     segments -> whole-sector image stores, better splat/warp coherence than 16x2 rows);
+//   * one CTA per 16x16 tile, one thread per pixel; warp w owns the compact 8x4 pixel block w (32-B row
+//     segments -> whole-sector image stores);
 //   * the tile's list is staged by the TMA engine (tile_stage.cuh): one contiguous, sector-aligned
 //     record per entry holding xy/conic/opacity AND all blended channels, double-buffered so staging
 //     overlaps blending; the blend loop reads them as warp-broadcast LDS.128;
-//   * the loop is kept warp-converged: per entry one ballot decides whether any lane blends, the
-//     out_observe count is warp-aggregated (one integer atomic per warp instead of one per pixel),
-//     and warps/CTAs whose pixels are all saturated leave via warp/CTA votes;
+//   * each warp visits only the entries whose footprint-mask bit for its block is set (cull.cu): one
+//     ballot per 32 entries yields the warp's private work list, walked with ffs — ~70 % of the
+//     (block, entry) pairs of the reference's loop are never touched;
+//   * no per-pixel `done` flag: a terminated pixel continues with T = 0, for which the reference's own
+//     test (T (1 - alpha) < 1e-4) keeps failing, and its final transmittance is parked in a second
+//     register; the out_observe count is warp-aggregated (one integer atomic per warp and entry);
 //   * thresholds (alpha < 1/255, T < 1e-4, T > 0.5) use the same fp32 expressions and full-precision
 //     expf as the reference so that n_contrib / final_T / out_observe are reproduced exactly.
 #include "kernels.cuh"
@@ -30,8 +33,9 @@ constexpr unsigned kFull = 0xffffffffu;
 template <int CT4>
 __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    using Stage = TileStage<RS>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    TileStage<RS> stage;
+    Stage stage;
     stage.init(smem_raw);
 
     const int tile = blockIdx.x;
@@ -46,9 +50,12 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
     const int n = (int)(range.y - range.x);
     const int nbatch = (n + STAGE_BATCH - 1) / STAGE_BATCH;
 
-    float T = 1.0f;
+    // A live pixel carries its transmittance in T.  When the reference would set `done`, T is parked in
+    // T_final and T becomes 0: from then on T * (1 - alpha) < 1e-4 holds for every candidate, i.e. the
+    // pixel keeps "terminating" without any state change — exactly the reference's behaviour of ignoring it.
+    float T = inside ? 1.0f : 0.0f;
+    float T_final = 1.0f;
     uint32_t last_contributor = 0;
-    bool done = !inside;
     float acc[CT4];
 #pragma unroll
     for (int c = 0; c < CT4; ++c) acc[c] = 0.f;
@@ -60,74 +67,67 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
 
     int issued = 0, consumed = 0;
     if (nbatch > 0) {
-        stage.issue(0, entry_of(0), p.point_list, p.records);
+        stage.issue(0, entry_of(0), p.point_list, p.masks, p.records);
         issued = 1;
     }
     for (int b = 0; b < nbatch; ++b) {
         if (b + 1 < nbatch) {
-            stage.issue(b + 1, entry_of(b + 1), p.point_list, p.records);
+            stage.issue(b + 1, entry_of(b + 1), p.point_list, p.masks, p.records);
             issued = b + 2;
         }
         stage.wait(b);
         consumed = b + 1;
 
-        const float* rb = stage.rec_buf(b);
-        const int* ib = stage.id_buf(b);
+        const uint32_t rec0 = stage.rec_addr(b), ids0 = stage.ids_addr(b), msk0 = stage.mask_addr(b);
         const int cnt = min(STAGE_BATCH, n - b * STAGE_BATCH);
-        if (!__all_sync(kFull, done)) {
-            for (int j = 0; j < cnt; ++j) {
-                const float4 h0 = *reinterpret_cast<const float4*>(rb + j * RS);      // x, y, conic.x, conic.y
-                const float2 h1 = *reinterpret_cast<const float2*>(rb + j * RS + 4);  // conic.z, opacity
-                bool blend = false;
-                float alpha = 0.f, test_T = 0.f;
-                if (!done) {
-                    const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
-                    const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-                    if (!(power > 0.0f)) {
-                        alpha = splat_alpha(h1.y, expf(power));
-                        if (!(alpha < 1.0f / 255.0f)) {
-                            test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-                            if (test_T < 0.0001f)
-                                done = true;
-                            else
-                                blend = true;
-                        }
-                    }
+        for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
+            if (__all_sync(kFull, T == 0.0f)) break;
+            // this warp's work list among the 32 entries of the chunk (slots >= cnt carry mask 0)
+            unsigned bits = __ballot_sync(kFull, (lds8u(msk0 + chunk * 32 + lane) >> warp) & 1u);
+            while (bits) {
+                const int j = chunk * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const uint32_t ra = rec0 + (uint32_t)j * Stage::kRecBytes;
+                const float4 h0 = lds128(ra);      // x, y, conic.x, conic.y
+                const float2 h1 = lds64(ra + 16);  // conic.z, opacity
+                const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
+                const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
+                const float alpha = splat_alpha(h1.y, expf(power));
+                const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+                const bool cand = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                const bool blend = cand && !(test_T < 0.0001f);
+                if (cand && !blend && T != 0.0f) {  // the reference's `done = true` (entry NOT blended)
+                    T_final = T;
+                    T = 0.0f;
                 }
-                const unsigned bm = __ballot_sync(kFull, blend);
-                if (bm == 0) {
-                    if (__all_sync(kFull, done)) break;
-                    continue;
-                }
+                const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
+                if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ids0 + j * 4)], __popc(om));
                 if (blend) {
                     const float w = alpha * T;
-                    const float4* ch = reinterpret_cast<const float4*>(rb + j * RS + REC_HEAD);
 #pragma unroll
                     for (int q = 0; q < CT4 / 4; ++q) {
-                        const float4 f = ch[q];
+                        const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
                         acc[4 * q + 0] += f.x * w;
                         acc[4 * q + 1] += f.y * w;
                         acc[4 * q + 2] += f.z * w;
                         acc[4 * q + 3] += f.w * w;
                     }
-                }
-                const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
-                if (om != 0 && lane == 0) atomicAdd(&p.out_observe[ib[j]], __popc(om));
-                if (blend) {
                     T = test_T;
                     last_contributor = (uint32_t)(b * STAGE_BATCH + j + 1);
                 }
             }
         }
         // CTA-wide vote; doubles as the barrier that frees buffer (b & 1) for batch b + 2
-        if (__syncthreads_and(done)) break;
+        if (__syncthreads_and(T == 0.0f)) break;
     }
     // never leave with bulk copies still in flight into this CTA's shared memory
     for (int b = consumed; b < issued; ++b) stage.wait(b);
+    if (T != 0.0f) T_final = T;  // never terminated
 
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
+        T = T_final;
         p.final_T[pix] = T;
         p.n_contrib[pix] = last_contributor;
 #pragma unroll

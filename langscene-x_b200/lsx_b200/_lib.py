@@ -120,7 +120,7 @@ def check(status, what):
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
 
 
-STAGES = ["preprocess_fwd", "depth_sort", "offsets_scan", "emit", "tile_sort", "tile_ranges", "render_fwd", "bwd_zero",
+STAGES = ["preprocess_fwd", "depth_sort", "offsets_scan", "emit", "tile_sort", "tile_ranges", "footprint_masks", "render_fwd", "bwd_zero",
           "render_bwd", "preprocess_bwd", "knn"]
 
 
