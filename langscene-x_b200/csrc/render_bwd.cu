@@ -163,11 +163,9 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
     const int n_eff = min(s_tile_max, n);
     const int nbatch = (n_eff + STAGE_BATCH - 1) / STAGE_BATCH;
 
-    float A = 0.f;  // <accumulated colour behind, upstream gradient>
-    float last_alpha = 0.f;
-    float last_s = 0.f;
-    const float ddelx_dx = 0.5 * p.W;
-    const float ddely_dy = 0.5 * p.H;
+    float Bacc = 0.f;  // <colour accumulated behind the current entry (inclusive), upstream gradient>
+    const float ddelx_dx = 0.5f * (float)p.W;
+    const float ddely_dy = 0.5f * (float)p.H;
     const uint32_t w_addr = smem_u32(&s_w[warp][0][0]);
     unsigned parity = 0;
 
@@ -202,69 +200,73 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
                 const bool blend = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
                 if (__ballot_sync(kFull, blend) == 0) continue;
 
-                float w = 0.f;
-                float v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                // per-lane terms; lanes that do not blend carry u = w = 0 so that every product below vanishes
+                float w = 0.f, u = 0.f;  // u = G * dL/dalpha
                 if (blend) {
-                    T = __fdiv_rn(T, __fadd_rn(1.f, -alpha));
+                    const float om = __fadd_rn(1.f, -alpha);  // in [0.01, 1]
+                    float r;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(om));
+                    r = __fmaf_rn(r, __fmaf_rn(-om, r, 1.0f), r);  // one Newton step: <= 1 ulp
+#ifdef LSX_BWD_EXACT_DIV
+                    T = __fdiv_rn(T, om);
+#else
+                    T *= r;
+#endif
                     w = alpha * T;
-                    float s = 0.f;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                     for (int q = 0; q < CT4 / 4; ++q) {
                         const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
-                        s += f.x * g[4 * q + 0];
-                        s += f.y * g[4 * q + 1];
-                        s += f.z * g[4 * q + 2];
-                        s += f.w * g[4 * q + 3];
+                        s0 += f.x * g[4 * q + 0];
+                        s1 += f.y * g[4 * q + 1];
+                        s2 += f.z * g[4 * q + 2];
+                        s3 += f.w * g[4 * q + 3];
                     }
-                    A = last_alpha * last_s + (1.f - last_alpha) * A;
-                    last_s = s;
-                    float dL_dalpha = (s - A) * T;
-                    last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
-
-                    const float dL_dG = h1.y * dL_dalpha;
-                    const float gdx = G * dx;
-                    const float gdy = G * dy;
-                    const float dG_ddelx = -gdx * h0.z - gdy * h0.w;
-                    const float dG_ddely = -gdy * h1.x - gdx * h0.w;
-                    const float mx = dL_dG * dG_ddelx * ddelx_dx;
-                    const float my = dL_dG * dG_ddely * ddely_dy;
-                    v[0] = mx;
-                    v[1] = my;
-                    v[2] = fabsf(mx);
-                    v[3] = fabsf(my);
-                    v[4] = -0.5f * gdx * dx * dL_dG;
-                    v[5] = -0.5f * gdx * dy * dL_dG;
-                    v[6] = -0.5f * gdy * dy * dL_dG;
-                    v[7] = G * dL_dalpha;
+                    const float s = (s0 + s1) + (s2 + s3);
+                    // A = <colour accumulated behind this entry, upstream gradient>; Bacc = the same including this entry
+                    const float dL_dalpha = (s - Bacc) * T - (T_final * r) * bg_dot;
+                    Bacc = alpha * s + (1.f - alpha) * Bacc;
+                    u = G * dL_dalpha;
                 }
+                const float ku = h1.y * u;  // opacity * G * dL/dalpha = G * dL/dG
+                const float kdx = ku * dx, kdy = ku * dy;
+                const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
+                const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
+                float v[8];
+                v[0] = mx;
+                v[1] = my;
+                v[2] = fabsf(mx);
+                v[3] = fabsf(my);
+                v[4] = -0.5f * kdx * dx;
+                v[5] = -0.5f * kdx * dy;
+                v[6] = -0.5f * kdy * dy;
+                v[7] = u;
 
                 // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
                 const uint32_t wa = w_addr + parity * 128u;
                 parity ^= 1u;
                 sts32(wa + lane * 4u, w);
                 __syncwarp();
-                float cg[NPASS];
+                float cg[NPASS][4];
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) cg[ps] = 0.f;
+                for (int ps = 0; ps < NPASS; ++ps) cg[ps][0] = cg[ps][1] = cg[ps][2] = cg[ps][3] = 0.f;
 #pragma unroll
                 for (int q4 = 0; q4 < 8; ++q4) {
                     const float4 wq = lds128(wa + q4 * 16);
 #pragma unroll
                     for (int ps = 0; ps < NPASS; ++ps) {
-                        cg[ps] += wq.x * gT[ps][4 * q4 + 0];
-                        cg[ps] += wq.y * gT[ps][4 * q4 + 1];
-                        cg[ps] += wq.z * gT[ps][4 * q4 + 2];
-                        cg[ps] += wq.w * gT[ps][4 * q4 + 3];
+                        cg[ps][0] += wq.x * gT[ps][4 * q4 + 0];
+                        cg[ps][1] += wq.y * gT[ps][4 * q4 + 1];
+                        cg[ps][2] += wq.z * gT[ps][4 * q4 + 2];
+                        cg[ps][3] += wq.w * gT[ps][4 * q4 + 3];
                     }
                 }
                 float* grec = p.grad_records + (size_t)lds32i(ids0 + j * 4) * GS;
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
                     const int c = ps * 32 + (int)lane;
-                    if (c < p.n_channels && cg[ps] != 0.f) atomicAdd(grec + c, cg[ps]);
+                    const float sum = (cg[ps][0] + cg[ps][1]) + (cg[ps][2] + cg[ps][3]);
+                    if (c < p.n_channels && sum != 0.f) atomicAdd(grec + c, sum);
                 }
                 // ---- geometry terms: 8 values -> lanes 0,4,...,28 ----
                 WarpTransposeReduce<8, 16>::run(v, lane);

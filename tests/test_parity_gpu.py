@@ -39,7 +39,7 @@ def _bit_equal(a, b):
     return bool((a.contiguous().view(torch.int32) == b.contiguous().view(torch.int32)).all())
 
 
-def _compare_all(fargs, grads, F, P, W, H, n_blend):
+def _compare_all(fargs, grads, F, P, W, H, n_blend, bwd_tol=BWD_TOL):
     ref = hz.ref_rast_for(F)
     if ref is None:
         pytest.skip("oracle/_ref not built")
@@ -81,7 +81,7 @@ def _compare_all(fargs, grads, F, P, W, H, n_blend):
         if rb[k].numel() > 1 and float(rb[k].abs().max()) > 0:
             spread = max(hz.rel_err(r2[k], rb[k]) for r2 in reruns)
             err = hz.rel_err(nb[k], rb[k])
-            assert err < max(BWD_TOL, 6 * spread), f"{k}: err {err:.3e}, reference self-spread {spread:.3e}"
+            assert err < max(bwd_tol, 6 * spread), f"{k}: err {err:.3e}, reference self-spread {spread:.3e}"
         else:
             assert float(nb[k].abs().max()) == 0.0 if nb[k].numel() else True, k
     return rf, nf
@@ -146,7 +146,13 @@ def test_edge_cases_match_reference():
     scene, cam, grads = _scene(64, W, H, F, seed=5, s_med=0.05)
     scene.means3D[:] = scene.means3D[0]
     fargs = hz.native_forward_args(scene, cam, bg, F)
-    _compare_all(fargs, grads, F, 64, W, H, 14)
+    # Gradient bound 5e-4 for this degenerate stack only (everything else in this file uses 1e-4): 64 splats on one
+    # pixel footprint with near-constant map channels make  <c_j - accumulated colour, dL/dpix>  a difference of two
+    # nearly equal numbers.  The reference rounds it per channel, this implementation as one dot product (see
+    # render_bwd.cu), so both carry O(1e-7 |s| / |difference|) noise of different sign, which the
+    # conic -> covariance -> scale/rotation chain amplifies (measured: means2D 4e-5, opacity 1e-5, rotations 2e-4).
+    # The reference is deterministic at this size, so its run-to-run spread cannot stand in for that noise.
+    _compare_all(fargs, grads, F, 64, W, H, 14, bwd_tol=5e-4)
 
 
 def test_empty_input():
