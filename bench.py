@@ -19,7 +19,6 @@ library's event hooks), `stats` (P_vis, R, S), `peaks` (measured FP32 / EX2 / RE
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -45,40 +44,51 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled every 100 ms DURING the timed regions, in-process through NVML
+    (spawning `nvidia-smi -lms` costs a driver initialisation that lands inside short timed regions and was
+    measured to stall kernel launches for 50-200 ms).  Started before the warm-up so that NVML is initialised
+    outside the timed region."""
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        self.rows, self.ok, self._stop = [], False, threading.Event()
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.thread = threading.Thread(target=self._run, daemon=True)
             self.thread.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)[:100]
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((sm, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self._stop.set()
+        self.thread.join(timeout=1.0)
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for _, r in self.rows:
+            bits |= r
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm)}
 
 
 def build_case(cfg_name, device, view_yaw=0.0, seed=0):
@@ -94,26 +104,31 @@ def build_case(cfg_name, device, view_yaw=0.0, seed=0):
     return c, scene, cam, grads, bg, am, fargs
 
 
-def time_loop(step_fn, steps, warmup, world):
-    """W warm-ups, then exactly K steps between barrier+synchronize pairs, CUDA events, max over ranks."""
+def time_loop(step_fn, steps, warmup, world, detail=None):
+    """W warm-ups, then exactly K steps between barrier+synchronize pairs, CUDA events, max over ranks.
+    `detail` (dict) receives the per-step median from one event per step (diagnostic only)."""
     for _ in range(warmup):
         step_fn()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
         step_fn()
-    e1.record()
+        ev[i + 1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if detail is not None:
+        per = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(steps))
+        detail["median_ms"] = per[len(per) // 2]
+        detail["max_ms"] = per[-1]
     return float(ms.item())
 
 
@@ -289,6 +304,7 @@ def main():
         mod = ops
     arena = GradArena.allocate(P, M, F, Fi, device) if world > 1 else None
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # runs through both timed regions
     # ---- device-resident timing ----------------------------------------------------------------------
     step = native_stepper(mod, fargs, grads, arena, world)
     fwd, bwd = step()
@@ -303,9 +319,8 @@ def main():
     del nbuf, fwd, bwd
 
     launches0 = _lib.kernel_launch_count()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms_total = time_loop(step, args.steps, warmup, world)
-    clocks = sampler.stop() if sampler else None
+    step_detail = {}
+    ms_total = time_loop(step, args.steps, warmup, world, step_detail)
     launches = (_lib.kernel_launch_count() - launches0) if args.impl == "new" else 0
     ms_step = ms_total / args.steps
     mpix = world * W * H / (ms_step * 1e-3) / 1e6
@@ -328,6 +343,7 @@ def main():
     else:
         estep, h2d, d2h = e2e_stepper(mod, fargs, grads, cam, pinned, arena)
     ms_e2e = time_loop(estep, args.steps, warmup, world) / args.steps
+    clocks = sampler.stop() if sampler else None
     e2e = {"value": world * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if args.impl == "new"
@@ -342,7 +358,8 @@ def main():
     Ct = 3 + F + Fi + 5
     out = {
         "metric": METRIC, "value": mpix, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "ms_per_step_median": step_detail.get("median_ms"), "ms_per_step_max": step_detail.get("max_ms"),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": args.impl,
         "config": {"workload": f"{args.config}: {P} Gaussians, {W}x{H}, SH degree 3, F={F} language + {Fi} instance + 5 map "
                                f"channels + plane depth, 1 view per GPU per step, fwd+bwd"

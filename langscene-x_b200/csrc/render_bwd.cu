@@ -14,8 +14,9 @@
 //     pixel's upstream gradient is carried as ONE scalar:  A <- a_prev * s_prev + (1 - a_prev) * A  with
 //     s = <feat[g], dL/dpix>.  That removes 2*Ct registers and ~3*Ct flops per blend compared with the
 //     per-channel form.
-//   * warp w owns the 8x4 pixel block w of the tile and visits only the list entries whose footprint-mask
-//     bit is set (cull.cu), back to front.
+//   * ONE WARP PER CTA: warp = one 8x4 pixel block of a tile; it stages (TMA, double-buffered, tile_stage.cuh)
+//     and visits only the list entries whose footprint-mask bit for its block is set (cull.cu), back to front,
+//     starting below the block's deepest contributor.  No CTA-wide barrier anywhere.
 //   * the channel gradients of one entry, dL/dfeat[c] = sum_pix (alpha T)_pix * dL/dpix[c], are an outer
 //     product over the warp's 32 pixels.  Each lane keeps TWO views of the block's upstream gradient in
 //     registers: its own pixel's channel vector (for s) and, transposed, channel `lane` of all 32 pixels.
@@ -25,8 +26,7 @@
 //     Only the 8 geometry terms (mean2D, |mean2D|, conic, opacity) go through a transposing butterfly.
 //     The reference issues Ct + 8 global atomics per (pixel, Gaussian); this kernel issues Ct + 8 per
 //     (32-pixel block, Gaussian), all into one contiguous 144-B record.
-//   * CTA-level skip of the list tail beyond the tile's deepest contributor, TMA-staged records
-//     (tile_stage.cuh), warp-ballot skip of entries no lane blends.
+//   * warp-ballot skip of entries no lane blends.
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
@@ -57,27 +57,21 @@ struct WarpTransposeReduce {
     }
 };
 
-__device__ __forceinline__ void sts32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-
-template <int CT4>
-__global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderParams p) {
+template <int CT4, int CHUNK>
+__global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     constexpr int GS = CT4 + 8;                // floats per packed gradient record
     constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
     constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
-    using Stage = TileStage<RS>;
+    using Stage = WarpStage<RS, CHUNK>;
+    static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int s_tile_max;
-    __shared__ __align__(16) float s_w[TILE_PIXELS / 32][2][32];  // per-warp weight exchange, double buffered
-    if (threadIdx.x == 0) s_tile_max = 0;
+    __shared__ __align__(16) float s_w[2][32];  // weight exchange, double buffered
 
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
-    const unsigned lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x;
     const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
     const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
@@ -139,10 +133,14 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
         }
     }
 
+    // deepest contributor of the block: list entries at or beyond it are never blended by any of its pixels
+    const int n_eff = min(__reduce_max_sync(kFull, last_contributor), n);
+    if (n_eff == 0) return;
+
     // ---- transposed view: gT[ps][q] = upstream gradient of channel (32 ps + lane) at pixel q of this block ----
     float gT[NPASS][32];
     {
-        float* ts = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 32 * TS;  // aliases the stage buffers (not yet live)
+        float* ts = reinterpret_cast<float*>(smem_raw);  // aliases the record buffers (not yet live)
 #pragma unroll
         for (int c = 0; c < CT4; ++c) ts[lane * TS + c] = g[c];
         __syncwarp();
@@ -152,144 +150,130 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_bwd_kernel(const RenderPar
 #pragma unroll
             for (int q = 0; q < 32; ++q) gT[ps][q] = (c < CT4) ? ts[q * TS + c] : 0.f;
         }
+        __syncwarp();
     }
-
-    // deepest contributor of the tile: list entries at or beyond it are never blended by any pixel
-    const int warp_max = __reduce_max_sync(kFull, last_contributor);
-    if (lane == 0 && warp_max > 0) atomicMax(&s_tile_max, warp_max);
-    __syncthreads();  // also: every warp is done with the transposition scratch
     Stage stage;
-    stage.init(smem_raw);  // contains a __syncthreads
-    const int n_eff = min(s_tile_max, n);
-    const int nbatch = (n_eff + STAGE_BATCH - 1) / STAGE_BATCH;
+    stage.init(smem_raw);
+    const int nrounds = (n_eff + CHUNK - 1) / CHUNK;
 
     float Bacc = 0.f;  // <colour accumulated behind the current entry (inclusive), upstream gradient>
     const float ddelx_dx = 0.5f * (float)p.W;
     const float ddely_dy = 0.5f * (float)p.H;
-    const uint32_t w_addr = smem_u32(&s_w[warp][0][0]);
+    const uint32_t w_addr = smem_u32(&s_w[0][0]);
     unsigned parity = 0;
 
-    auto entry_of = [&](int b) -> long long {
-        const int e = n_eff - 1 - (b * STAGE_BATCH + (int)threadIdx.x);
-        return e >= 0 ? (long long)range.x + e : -1;
+    // round r covers list indices n_eff-1 - (r*CHUNK + lane), i.e. back to front
+    auto entry_of = [&](int r) -> long long {
+        const int e = n_eff - 1 - (r * CHUNK + (int)lane);
+        return (lane < CHUNK && e >= 0) ? (long long)range.x + e : -1;
     };
 
-    if (nbatch > 0) stage.issue(0, entry_of(0), p.point_list, p.masks, p.records);
-    for (int b = 0; b < nbatch; ++b) {
-        if (b + 1 < nbatch) stage.issue(b + 1, entry_of(b + 1), p.point_list, p.masks, p.records);
-        stage.wait(b);
-        const uint32_t rec0 = stage.rec_addr(b), ids0 = stage.ids_addr(b), msk0 = stage.mask_addr(b);
-        const int cnt = min(STAGE_BATCH, n_eff - b * STAGE_BATCH);
-        const int e0 = n_eff - 1 - b * STAGE_BATCH;  // list index of slot 0
+    unsigned bits_next = stage.issue(0, entry_of(0), warp, p.point_list, p.masks, p.records);
+    for (int r = 0; r < nrounds; ++r) {
+        unsigned bits = bits_next;
+        if (r + 1 < nrounds) bits_next = stage.issue((r + 1) & 1, entry_of(r + 1), warp, p.point_list, p.masks, p.records);
+        stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
+        uint32_t ra = stage.rec_addr(r & 1) - Stage::kRecBytes;
+        uint32_t ia = stage.ids_addr(r & 1) - 4;
+        const int e0 = n_eff - 1 - r * CHUNK;  // list index of lane 0's candidate
 
-        for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
-            // slots of this chunk that can touch this warp's block and lie below its deepest contributor
-            const int slot = chunk * 32 + (int)lane;
-            unsigned bits = __ballot_sync(kFull, ((lds8u(msk0 + slot) >> warp) & 1u) && (e0 - slot < warp_max));
-            while (bits) {
-                const int j = chunk * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int e = e0 - j;
-                const uint32_t ra = rec0 + (uint32_t)j * Stage::kRecBytes;
-                const float4 h0 = lds128(ra);
-                const float2 h1 = lds64(ra + 16);
-                const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
-                const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-                const float G = expf(power);
-                const float alpha = splat_alpha(h1.y, G);
-                const bool blend = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                if (__ballot_sync(kFull, blend) == 0) continue;
+        while (bits) {
+            const int e = e0 - (__ffs(bits) - 1);
+            bits &= bits - 1;
+            ra += Stage::kRecBytes;
+            ia += 4;
+            const float4 h0 = lds128(ra);
+            const float2 h1 = lds64(ra + 16);
+            const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
+            const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
+            const float G = expf(power);
+            const float alpha = splat_alpha(h1.y, G);
+            const bool blend = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            if (__ballot_sync(kFull, blend) == 0) continue;
 
-                // per-lane terms; lanes that do not blend carry u = w = 0 so that every product below vanishes
-                float w = 0.f, u = 0.f;  // u = G * dL/dalpha
-                if (blend) {
-                    const float om = __fadd_rn(1.f, -alpha);  // in [0.01, 1]
-                    float r;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(om));
-                    r = __fmaf_rn(r, __fmaf_rn(-om, r, 1.0f), r);  // one Newton step: <= 1 ulp
-#ifdef LSX_BWD_EXACT_DIV
-                    T = __fdiv_rn(T, om);
-#else
-                    T *= r;
-#endif
-                    w = alpha * T;
-                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            // per-lane terms; lanes that do not blend carry u = w = 0 so that every product below vanishes
+            float w = 0.f, u = 0.f;  // u = G * dL/dalpha
+            if (blend) {
+                const float om = __fadd_rn(1.f, -alpha);  // in [0.01, 1]
+                float rcp;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(om));
+                rcp = __fmaf_rn(rcp, __fmaf_rn(-om, rcp, 1.0f), rcp);  // one Newton step: <= 1 ulp
+                T *= rcp;
+                w = alpha * T;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-                    for (int q = 0; q < CT4 / 4; ++q) {
-                        const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
-                        s0 += f.x * g[4 * q + 0];
-                        s1 += f.y * g[4 * q + 1];
-                        s2 += f.z * g[4 * q + 2];
-                        s3 += f.w * g[4 * q + 3];
-                    }
-                    const float s = (s0 + s1) + (s2 + s3);
-                    // A = <colour accumulated behind this entry, upstream gradient>; Bacc = the same including this entry
-                    const float dL_dalpha = (s - Bacc) * T - (T_final * r) * bg_dot;
-                    Bacc = alpha * s + (1.f - alpha) * Bacc;
-                    u = G * dL_dalpha;
+                for (int q = 0; q < CT4 / 4; ++q) {
+                    const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
+                    s0 += f.x * g[4 * q + 0];
+                    s1 += f.y * g[4 * q + 1];
+                    s2 += f.z * g[4 * q + 2];
+                    s3 += f.w * g[4 * q + 3];
                 }
-                const float ku = h1.y * u;  // opacity * G * dL/dalpha = G * dL/dG
-                const float kdx = ku * dx, kdy = ku * dy;
-                const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
-                const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
-                float v[8];
-                v[0] = mx;
-                v[1] = my;
-                v[2] = fabsf(mx);
-                v[3] = fabsf(my);
-                v[4] = -0.5f * kdx * dx;
-                v[5] = -0.5f * kdx * dy;
-                v[6] = -0.5f * kdy * dy;
-                v[7] = u;
+                const float s = (s0 + s1) + (s2 + s3);
+                const float dL_dalpha = (s - Bacc) * T - (T_final * rcp) * bg_dot;
+                Bacc = alpha * s + (1.f - alpha) * Bacc;
+                u = G * dL_dalpha;
+            }
+            const float ku = h1.y * u;  // opacity * G * dL/dalpha = G * dL/dG
+            const float kdx = ku * dx, kdy = ku * dy;
+            const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
+            const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
+            float v[8];
+            v[0] = mx;
+            v[1] = my;
+            v[2] = fabsf(mx);
+            v[3] = fabsf(my);
+            v[4] = -0.5f * kdx * dx;
+            v[5] = -0.5f * kdx * dy;
+            v[6] = -0.5f * kdy * dy;
+            v[7] = u;
 
-                // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
-                const uint32_t wa = w_addr + parity * 128u;
-                parity ^= 1u;
-                sts32(wa + lane * 4u, w);
-                __syncwarp();
-                float cg[NPASS][4];
+            // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
+            const uint32_t wa = w_addr + parity * 128u;
+            parity ^= 1u;
+            sts32(wa + lane * 4u, w);
+            __syncwarp();
+            float cg[NPASS][4];
 #pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) cg[ps][0] = cg[ps][1] = cg[ps][2] = cg[ps][3] = 0.f;
+            for (int ps = 0; ps < NPASS; ++ps) cg[ps][0] = cg[ps][1] = cg[ps][2] = cg[ps][3] = 0.f;
 #pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    const float4 wq = lds128(wa + q4 * 16);
-#pragma unroll
-                    for (int ps = 0; ps < NPASS; ++ps) {
-                        cg[ps][0] += wq.x * gT[ps][4 * q4 + 0];
-                        cg[ps][1] += wq.y * gT[ps][4 * q4 + 1];
-                        cg[ps][2] += wq.z * gT[ps][4 * q4 + 2];
-                        cg[ps][3] += wq.w * gT[ps][4 * q4 + 3];
-                    }
-                }
-                float* grec = p.grad_records + (size_t)lds32i(ids0 + j * 4) * GS;
+            for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 wq = lds128(wa + q4 * 16);
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
-                    const int c = ps * 32 + (int)lane;
-                    const float sum = (cg[ps][0] + cg[ps][1]) + (cg[ps][2] + cg[ps][3]);
-                    if (c < p.n_channels && sum != 0.f) atomicAdd(grec + c, sum);
+                    cg[ps][0] += wq.x * gT[ps][4 * q4 + 0];
+                    cg[ps][1] += wq.y * gT[ps][4 * q4 + 1];
+                    cg[ps][2] += wq.z * gT[ps][4 * q4 + 2];
+                    cg[ps][3] += wq.w * gT[ps][4 * q4 + 3];
                 }
-                // ---- geometry terms: 8 values -> lanes 0,4,...,28 ----
-                WarpTransposeReduce<8, 16>::run(v, lane);
-                if ((lane & 3u) == 0u && v[0] != 0.f) atomicAdd(grec + CT4 + (lane >> 2), v[0]);
             }
+            float* grec = p.grad_records + (size_t)lds32i(ia) * GS;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps) {
+                const int c = ps * 32 + (int)lane;
+                const float sum = (cg[ps][0] + cg[ps][1]) + (cg[ps][2] + cg[ps][3]);
+                if (c < p.n_channels && sum != 0.f) atomicAdd(grec + c, sum);
+            }
+            // ---- geometry terms: 8 values -> lanes 0,4,...,28 ----
+            WarpTransposeReduce<8, 16>::run(v, lane);
+            if ((lane & 3u) == 0u && v[0] != 0.f) atomicAdd(grec + CT4 + (lane >> 2), v[0]);
         }
-        __syncthreads();  // frees buffer (b & 1) for batch b + 2
     }
+}
+
+template <int CT4, int CHUNK>
+int launch_bwd_tc(const RenderParams& p, cudaStream_t stream, bool debug) {
+    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    const size_t smem = WarpStage<RS, CHUNK>::kSmemBytes;
+    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
+    render_bwd_kernel<CT4, CHUNK><<<(unsigned)blocks, 32, smem, stream>>>(p);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
 }
 
 template <int CT4>
 int launch_bwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
-    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    const size_t smem = TileStage<RS>::kSmemBytes;
-    static bool configured = false;
-    if (!configured) {
-        LSX_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel<CT4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int tiles = (int)(p.grid_x * p.grid_y);
-    render_bwd_kernel<CT4><<<tiles, TILE_PIXELS, smem, stream>>>(p);
-    LSX_KERNEL_OK(stream, debug);
-    return 0;
+    return launch_bwd_tc<CT4, 32>(p, stream, debug);
 }
 
 }  // namespace

@@ -8,19 +8,21 @@
 //   plane_depth = A4 / -(A0*ray.x + A1*ray.y + A2 + 1e-8) evaluated in double.
 //
 // B200 design
-//   * one CTA per 16x16 tile, one thread per pixel; warp w owns the compact 8x4 pixel block w (32-B row
-//     segments -> whole-sector image stores);
-//   * the tile's list is staged by the TMA engine (tile_stage.cuh): one contiguous, sector-aligned
-//     record per entry holding xy/conic/opacity AND all blended channels, double-buffered so staging
-//     overlaps blending; the blend loop reads them as warp-broadcast LDS.128;
-//   * each warp visits only the entries whose footprint-mask bit for its block is set (cull.cu): one
-//     ballot per 32 entries yields the warp's private work list, walked with ffs — ~70 % of the
-//     (block, entry) pairs of the reference's loop are never touched;
+//   * ONE WARP PER CTA: warp = one 8x4 pixel block of a 16x16 tile (32-B row segments -> whole-sector image
+//     stores); 8 consecutive CTAs share a tile list.  No CTA-wide barrier exists, finished blocks free their
+//     slot immediately, and up to 32 blocks are resident per SM;
+//   * each warp stages only the list entries whose footprint-mask bit for its block is set (cull.cu,
+//     tile_stage.cuh): ~70 % of the (block, entry) pairs of the reference's loop are never touched.  Staging is
+//     done by the TMA engine, one contiguous sector-aligned record per entry holding xy/conic/opacity AND all
+//     blended channels, double-buffered so the copies overlap blending; the blend loop reads them as
+//     warp-broadcast LDS.128;
 //   * no per-pixel `done` flag: a terminated pixel continues with T = 0, for which the reference's own
 //     test (T (1 - alpha) < 1e-4) keeps failing, and its final transmittance is parked in a second
 //     register; the out_observe count is warp-aggregated (one integer atomic per warp and entry);
 //   * thresholds (alpha < 1/255, T < 1e-4, T > 0.5) use the same fp32 expressions and full-precision
 //     expf as the reference so that n_contrib / final_T / out_observe are reproduced exactly.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
@@ -30,17 +32,25 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int CT4>
-__global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderParams p) {
+inline int tune_chunk() {  // LSX_FWD_CHUNK=32 selects the 32-entry rounds (experiments only)
+    static const int v = [] {
+        const char* e = getenv("LSX_FWD_CHUNK");
+        return e ? atoi(e) : 16;
+    }();
+    return v;
+}
+
+template <int CT4, int CHUNK>
+__global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    using Stage = TileStage<RS>;
+    using Stage = WarpStage<RS, CHUNK>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage stage;
     stage.init(smem_raw);
 
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x;
     const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
     const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
     const bool inside = px < p.W && py < p.H;
@@ -48,7 +58,7 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
 
     const uint2 range = p.ranges[tile];
     const int n = (int)(range.y - range.x);
-    const int nbatch = (n + STAGE_BATCH - 1) / STAGE_BATCH;
+    const int nrounds = (n + CHUNK - 1) / CHUNK;
 
     // A live pixel carries its transmittance in T.  When the reference would set `done`, T is parked in
     // T_final and T becomes 0: from then on T * (1 - alpha) < 1e-4 holds for every candidate, i.e. the
@@ -60,68 +70,65 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
 #pragma unroll
     for (int c = 0; c < CT4; ++c) acc[c] = 0.f;
 
-    auto entry_of = [&](int b) -> long long {
-        const int e = b * STAGE_BATCH + (int)threadIdx.x;
-        return e < n ? (long long)range.x + e : -1;
+    auto entry_of = [&](int r) -> long long {
+        const int e = r * CHUNK + lane;
+        return (lane < CHUNK && e < n) ? (long long)range.x + e : -1;
     };
 
+    unsigned bits_next = 0;
     int issued = 0, consumed = 0;
-    if (nbatch > 0) {
-        stage.issue(0, entry_of(0), p.point_list, p.masks, p.records);
+    if (nrounds > 0 && !__all_sync(kFull, T == 0.0f)) {
+        bits_next = stage.issue(0, entry_of(0), warp, p.point_list, p.masks, p.records);
         issued = 1;
     }
-    for (int b = 0; b < nbatch; ++b) {
-        if (b + 1 < nbatch) {
-            stage.issue(b + 1, entry_of(b + 1), p.point_list, p.masks, p.records);
-            issued = b + 2;
+    for (int r = 0; r < issued; ++r) {
+        unsigned bits = bits_next;
+        if (r + 1 < nrounds) {
+            bits_next = stage.issue((r + 1) & 1, entry_of(r + 1), warp, p.point_list, p.masks, p.records);
+            issued = r + 2;
         }
-        stage.wait(b);
-        consumed = b + 1;
+        stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
+        consumed = r + 1;
 
-        const uint32_t rec0 = stage.rec_addr(b), ids0 = stage.ids_addr(b), msk0 = stage.mask_addr(b);
-        const int cnt = min(STAGE_BATCH, n - b * STAGE_BATCH);
-        for (int chunk = 0; chunk * 32 < cnt; ++chunk) {
-            if (__all_sync(kFull, T == 0.0f)) break;
-            // this warp's work list among the 32 entries of the chunk (slots >= cnt carry mask 0)
-            unsigned bits = __ballot_sync(kFull, (lds8u(msk0 + chunk * 32 + lane) >> warp) & 1u);
-            while (bits) {
-                const int j = chunk * 32 + __ffs(bits) - 1;
-                bits &= bits - 1;
-                const uint32_t ra = rec0 + (uint32_t)j * Stage::kRecBytes;
-                const float4 h0 = lds128(ra);      // x, y, conic.x, conic.y
-                const float2 h1 = lds64(ra + 16);  // conic.z, opacity
-                const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
-                const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-                const float alpha = splat_alpha(h1.y, expf(power));
-                const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-                const bool cand = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-                const bool blend = cand && !(test_T < 0.0001f);
-                if (cand && !blend && T != 0.0f) {  // the reference's `done = true` (entry NOT blended)
-                    T_final = T;
-                    T = 0.0f;
-                }
-                const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
-                if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ids0 + j * 4)], __popc(om));
-                if (blend) {
-                    const float w = alpha * T;
-#pragma unroll
-                    for (int q = 0; q < CT4 / 4; ++q) {
-                        const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
-                        acc[4 * q + 0] += f.x * w;
-                        acc[4 * q + 1] += f.y * w;
-                        acc[4 * q + 2] += f.z * w;
-                        acc[4 * q + 3] += f.w * w;
-                    }
-                    T = test_T;
-                    last_contributor = (uint32_t)(b * STAGE_BATCH + j + 1);
-                }
+        uint32_t ra = stage.rec_addr(r & 1);
+        uint32_t ia = stage.ids_addr(r & 1);
+        while (bits) {
+            const int pos = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const float4 h0 = lds128(ra);      // x, y, conic.x, conic.y
+            const float2 h1 = lds64(ra + 16);  // conic.z, opacity
+            const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
+            const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
+            const float alpha = splat_alpha(h1.y, expf(power));
+            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+            const bool cand = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            const bool blend = cand && !(test_T < 0.0001f);
+            if (cand && !blend && T != 0.0f) {  // the reference's `done = true` (entry NOT blended)
+                T_final = T;
+                T = 0.0f;
             }
+            const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
+            if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
+            if (blend) {
+                const float w = alpha * T;
+#pragma unroll
+                for (int q = 0; q < CT4 / 4; ++q) {
+                    const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
+                    acc[4 * q + 0] += f.x * w;
+                    acc[4 * q + 1] += f.y * w;
+                    acc[4 * q + 2] += f.z * w;
+                    acc[4 * q + 3] += f.w * w;
+                }
+                T = test_T;
+                last_contributor = (uint32_t)(r * CHUNK + pos + 1);
+            }
+            ra += Stage::kRecBytes;
+            ia += 4;
         }
-        // CTA-wide vote; doubles as the barrier that frees buffer (b & 1) for batch b + 2
-        if (__syncthreads_and(T == 0.0f)) break;
+        if (__all_sync(kFull, T == 0.0f)) break;  // every pixel of the block is saturated
     }
     // never leave with bulk copies still in flight into this CTA's shared memory
-    for (int b = consumed; b < issued; ++b) stage.wait(b);
+    for (int r = consumed; r < issued; ++r) stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
     if (T != 0.0f) T_final = T;  // never terminated
 
     if (inside) {
@@ -162,19 +169,20 @@ __global__ void __launch_bounds__(TILE_PIXELS) render_fwd_kernel(const RenderPar
     }
 }
 
-template <int CT4>
-int launch_fwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
+template <int CT4, int CHUNK>
+int launch_fwd_tc(const RenderParams& p, cudaStream_t stream, bool debug) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    const size_t smem = TileStage<RS>::kSmemBytes;
-    static bool configured = false;  // per-instantiation; benign race (same value)
-    if (!configured) {
-        LSX_CUDA_OK(cudaFuncSetAttribute(render_fwd_kernel<CT4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    const int tiles = (int)(p.grid_x * p.grid_y);
-    render_fwd_kernel<CT4><<<tiles, TILE_PIXELS, smem, stream>>>(p);
+    const size_t smem = WarpStage<RS, CHUNK>::kSmemBytes;
+    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
+    render_fwd_kernel<CT4, CHUNK><<<(unsigned)blocks, 32, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
+}
+
+template <int CT4>
+int launch_fwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
+    // rounds of 16 list entries keep a block's staging buffers at ~5 KB, so 32 blocks fit on an SM
+    return tune_chunk() == 32 ? launch_fwd_tc<CT4, 32>(p, stream, debug) : launch_fwd_tc<CT4, 16>(p, stream, debug);
 }
 
 }  // namespace

@@ -1,18 +1,17 @@
-// tile_stage.cuh — double-buffered staging of a tile's Gaussian list into shared memory.
+// tile_stage.cuh — per-warp, double-buffered staging of a tile's Gaussian list into shared memory.
 //
-// A batch is STAGE_BATCH list entries.  For each entry one thread reads the Gaussian index and the
-// sub-tile footprint mask (cull.cu) from the sorted list and issues ONE bulk copy (TMA engine,
-// cp.async.bulk -> UBLKCP) of that Gaussian's packed, sector-aligned record into the batch buffer,
-// signalling an mbarrier with the byte count.  Two buffers alternate so the copies of batch b+1 are in
-// flight while batch b is blended.  Consumers address the buffers through 32-bit shared-window
-// addresses (ld.shared with register + immediate operands, no generic-pointer arithmetic in the loops).
+// The render kernels run ONE WARP PER CTA: warp = one 8x4 pixel block of a 16x16 tile.  A round covers CHUNK
+// consecutive entries of the tile's sorted list: each lane reads one entry's sub-tile footprint mask (cull.cu);
+// a ballot of "my block's bit is set" is the warp's work list for the round, and every surviving lane issues ONE
+// bulk copy (TMA engine, cp.async.bulk -> UBLKCP) of its Gaussian's packed, sector-aligned record into the next
+// free slot of the round's buffer, signalling the buffer's mbarrier with the byte count.  Two buffers alternate,
+// so the copies of round r+1 are in flight while round r is blended; there is no CTA-wide barrier anywhere.
+// Consumers address the buffers through 32-bit shared-window addresses (ld.shared with register + immediate).
 #pragma once
 #include "async_copy.cuh"
 #include "common.cuh"
 
 namespace lsx {
-
-constexpr int STAGE_BATCH = 128;
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
@@ -29,19 +28,19 @@ __device__ __forceinline__ int lds32i(uint32_t addr) {
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned lds8u(uint32_t addr) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-template <int RS>  // record stride in floats
-struct TileStage {
+constexpr unsigned kFullMask = 0xffffffffu;
+
+template <int RS, int CHUNK>  // record stride in floats; list entries per round (<= 32)
+struct WarpStage {
+    static_assert(CHUNK == 8 || CHUNK == 16 || CHUNK == 32, "CHUNK must be 8, 16 or 32");
     static constexpr int kRecBytes = RS * 4;
-    static constexpr int kRecBuf = STAGE_BATCH * kRecBytes;                 // bytes of one record buffer
-    static constexpr int kIdsOff = 2 * kRecBuf;                             // int   ids  [2][STAGE_BATCH]
-    static constexpr int kMaskOff = kIdsOff + 2 * STAGE_BATCH * 4;          // uint8 mask [2][STAGE_BATCH]
-    static constexpr int kBarOff = kMaskOff + 2 * STAGE_BATCH;              // u64   bar  [2]
+    static constexpr int kBufBytes = CHUNK * kRecBytes;          // one record buffer
+    static constexpr int kIdsOff = 2 * kBufBytes;                // int ids [2][CHUNK]
+    static constexpr int kBarOff = kIdsOff + 2 * CHUNK * 4;      // u64 bar [2]
     static constexpr size_t kSmemBytes = kBarOff + 2 * sizeof(uint64_t);
 
     unsigned char* base;  // generic pointer (producer side)
@@ -49,43 +48,42 @@ struct TileStage {
 
     __device__ __forceinline__ uint64_t* bar(int buf) const { return reinterpret_cast<uint64_t*>(base + kBarOff) + buf; }
 
+    // one warp per CTA: all 32 threads call this
     __device__ __forceinline__ void init(unsigned char* smem) {
         base = smem;
         sbase = smem_u32(smem);
         if (threadIdx.x == 0) {
-            mbar_init(bar(0), STAGE_BATCH);
-            mbar_init(bar(1), STAGE_BATCH);
+            mbar_init(bar(0), 1);
+            mbar_init(bar(1), 1);
             mbar_init_fence();
         }
-        __syncthreads();
+        __syncwarp();
     }
 
-    // Issue the copies of batch b.  `entry` = position in point_list for this thread's slot, or -1.
-    // Must be called by (at least) threads 0..STAGE_BATCH-1 of the block, after every thread has finished
-    // reading the buffer (b & 1) from batch b-2 (i.e. after a __syncthreads).
-    __device__ __forceinline__ void issue(int b, long long entry, const uint32_t* __restrict__ point_list,
-                                          const uint8_t* __restrict__ masks, const float* __restrict__ records) {
-        if (threadIdx.x < STAGE_BATCH) {
-            const int buf = b & 1;
-            const int slot = buf * STAGE_BATCH + threadIdx.x;
-            if (entry >= 0) {
-                const int id = (int)__ldg(point_list + entry);
-                reinterpret_cast<int*>(base + kIdsOff)[slot] = id;
-                (base + kMaskOff)[slot] = __ldg(masks + entry);
-                mbar_arrive_expect_tx(bar(buf), kRecBytes);
-                bulk_copy_g2s(base + (size_t)slot * kRecBytes, records + (size_t)id * RS, kRecBytes, bar(buf));
-            } else {
-                (base + kMaskOff)[slot] = 0;
-                mbar_arrive(bar(buf));
-            }
+    // Stage the surviving entries of one round into buffer `buf`.  `entry` = absolute position in point_list /
+    // masks of this lane's candidate, or -1 (lanes >= CHUNK and positions outside the list).  Returns the ballot
+    // of surviving lanes: survivor number k (in lane order) occupies slot k.
+    __device__ __forceinline__ unsigned issue(int buf, long long entry, int block_bit, const uint32_t* __restrict__ point_list,
+                                              const uint8_t* __restrict__ masks, const float* __restrict__ records) {
+        const unsigned lane = threadIdx.x;
+        bool mine = false;
+        if (entry >= 0) mine = ((__ldg(masks + entry) >> block_bit) & 1u) != 0u;
+        const unsigned bits = __ballot_sync(kFullMask, mine);
+        if (mine) {
+            const int slot = __popc(bits & ((1u << lane) - 1u));
+            const int id = (int)__ldg(point_list + entry);
+            reinterpret_cast<int*>(base + kIdsOff)[buf * CHUNK + slot] = id;
+            bulk_copy_g2s(base + (size_t)buf * kBufBytes + (size_t)slot * kRecBytes, records + (size_t)id * RS, kRecBytes,
+                          bar(buf));
         }
+        if (lane == 0) mbar_arrive_expect_tx(bar(buf), (uint32_t)__popc(bits) * kRecBytes);
+        __syncwarp();  // ids visible to the whole warp
+        return bits;
     }
 
-    __device__ __forceinline__ void wait(int b) { mbar_wait(bar(b & 1), (uint32_t)((b >> 1) & 1)); }
-    // shared-window addresses of batch b's arrays
-    __device__ __forceinline__ uint32_t rec_addr(int b) const { return sbase + (uint32_t)((b & 1) * kRecBuf); }
-    __device__ __forceinline__ uint32_t ids_addr(int b) const { return sbase + (uint32_t)(kIdsOff + (b & 1) * STAGE_BATCH * 4); }
-    __device__ __forceinline__ uint32_t mask_addr(int b) const { return sbase + (uint32_t)(kMaskOff + (b & 1) * STAGE_BATCH); }
+    __device__ __forceinline__ void wait(int buf, uint32_t parity) { mbar_wait(bar(buf), parity); }
+    __device__ __forceinline__ uint32_t rec_addr(int buf) const { return sbase + (uint32_t)(buf * kBufBytes); }
+    __device__ __forceinline__ uint32_t ids_addr(int buf) const { return sbase + (uint32_t)(kIdsOff + buf * CHUNK * 4); }
 };
 
 }  // namespace lsx
