@@ -17,6 +17,7 @@ library's event hooks), `stats` (P_vis, R, S), `peaks` (measured FP32 / EX2 / RE
 --impl reference-cpu   the CPU restatement (oracle/) on all host threads on a bounded sample.
 """
 import argparse
+import gc
 import json
 import os
 import sys
@@ -51,6 +52,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.ok, self._stop = [], False, threading.Event()
+        self.call_ms, self.period = 0.0, float(os.environ.get("LSX_BENCH_SAMPLE_PERIOD", "0.1"))
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -67,15 +69,19 @@ class ClockSampler:
         nv = self.nv
         while not self._stop.is_set():
             try:
+                t0 = time.perf_counter()
                 sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                t1 = time.perf_counter()
                 try:
                     reasons = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:  # noqa: BLE001
                     reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                t2 = time.perf_counter()
                 self.rows.append((sm, reasons))
+                self.call_ms = max(self.call_ms, (t1 - t0) * 1e3, (t2 - t1) * 1e3)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(self.period)
 
     def stop(self):
         if not self.ok:
@@ -88,7 +94,8 @@ class ClockSampler:
             bits |= r
         names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_sm,
-                "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm)}
+                "reasons": [n for b, n in names.items() if bits & b], "samples": len(sm),
+                "nvml_call_ms_max": round(self.call_ms, 3)}
 
 
 def build_case(cfg_name, device, view_yaw=0.0, seed=0):
@@ -114,11 +121,17 @@ def time_loop(step_fn, steps, warmup, world, detail=None):
         dist.barrier()
         torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    # The step has a host round trip (num_rendered), so a stop-the-world pass of CPython's cyclic collector over the
+    # torch-sized heap (measured: 100-175 ms, once every few hundred steps) would land inside a 100 ms timed region.
+    # Collect now, keep the collector off while timing (reference-counted frees, i.e. all tensor frees, still happen).
+    gc.collect()
+    gc.disable()
     ev[0].record()
     for i in range(steps):
         step_fn()
         ev[i + 1].record()
     torch.cuda.synchronize()
+    gc.enable()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()

@@ -168,10 +168,15 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
         return (lane < CHUNK && e >= 0) ? (long long)range.x + e : -1;
     };
 
-    unsigned bits_next = stage.issue(0, entry_of(0), warp, p.point_list, p.masks, p.records);
+    stage.prefetch(entry_of(0), p.point_list, p.masks);
+    unsigned bits_next = stage.issue(0, warp, p.records);
+    stage.prefetch(entry_of(1), p.point_list, p.masks);
     for (int r = 0; r < nrounds; ++r) {
         unsigned bits = bits_next;
-        if (r + 1 < nrounds) bits_next = stage.issue((r + 1) & 1, entry_of(r + 1), warp, p.point_list, p.masks, p.records);
+        if (r + 1 < nrounds) {
+            bits_next = stage.issue((r + 1) & 1, warp, p.records);
+            stage.prefetch(entry_of(r + 2), p.point_list, p.masks);
+        }
         stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
         uint32_t ra = stage.rec_addr(r & 1) - Stage::kRecBytes;
         uint32_t ia = stage.ids_addr(r & 1) - 4;

@@ -78,14 +78,17 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     unsigned bits_next = 0;
     int issued = 0, consumed = 0;
     if (nrounds > 0 && !__all_sync(kFull, T == 0.0f)) {
-        bits_next = stage.issue(0, entry_of(0), warp, p.point_list, p.masks, p.records);
+        stage.prefetch(entry_of(0), p.point_list, p.masks);
+        bits_next = stage.issue(0, warp, p.records);
         issued = 1;
+        stage.prefetch(entry_of(1), p.point_list, p.masks);
     }
     for (int r = 0; r < issued; ++r) {
         unsigned bits = bits_next;
         if (r + 1 < nrounds) {
-            bits_next = stage.issue((r + 1) & 1, entry_of(r + 1), warp, p.point_list, p.masks, p.records);
+            bits_next = stage.issue((r + 1) & 1, warp, p.records);
             issued = r + 2;
+            stage.prefetch(entry_of(r + 2), p.point_list, p.masks);
         }
         stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
         consumed = r + 1;

@@ -60,21 +60,32 @@ struct WarpStage {
         __syncwarp();
     }
 
-    // Stage the surviving entries of one round into buffer `buf`.  `entry` = absolute position in point_list /
-    // masks of this lane's candidate, or -1 (lanes >= CHUNK and positions outside the list).  Returns the ballot
-    // of surviving lanes: survivor number k (in lane order) occupies slot k.
-    __device__ __forceinline__ unsigned issue(int buf, long long entry, int block_bit, const uint32_t* __restrict__ point_list,
-                                              const uint8_t* __restrict__ masks, const float* __restrict__ records) {
+    // Staging is software-pipelined: prefetch() loads the footprint mask and the Gaussian index of this lane's
+    // candidate one round ahead (plain global loads, latency off the critical path); issue() consumes the
+    // prefetched pair, stages the surviving entries of the round into buffer `buf` and returns the ballot of
+    // surviving lanes: survivor number k (in lane order) occupies slot k.
+    // `entry` = absolute position in point_list / masks of this lane's candidate, or -1 (lanes >= CHUNK and
+    // positions outside the list).
+    unsigned pre_mask;
+    int pre_id;
+    __device__ __forceinline__ void prefetch(long long entry, const uint32_t* __restrict__ point_list,
+                                             const uint8_t* __restrict__ masks) {
+        pre_mask = 0u;
+        pre_id = 0;
+        if (entry >= 0) {
+            pre_mask = __ldg(masks + entry);
+            pre_id = (int)__ldg(point_list + entry);
+        }
+    }
+    __device__ __forceinline__ unsigned issue(int buf, int block_bit, const float* __restrict__ records) {
         const unsigned lane = threadIdx.x;
-        bool mine = false;
-        if (entry >= 0) mine = ((__ldg(masks + entry) >> block_bit) & 1u) != 0u;
+        const bool mine = ((pre_mask >> block_bit) & 1u) != 0u;
         const unsigned bits = __ballot_sync(kFullMask, mine);
         if (mine) {
             const int slot = __popc(bits & ((1u << lane) - 1u));
-            const int id = (int)__ldg(point_list + entry);
-            reinterpret_cast<int*>(base + kIdsOff)[buf * CHUNK + slot] = id;
-            bulk_copy_g2s(base + (size_t)buf * kBufBytes + (size_t)slot * kRecBytes, records + (size_t)id * RS, kRecBytes,
-                          bar(buf));
+            reinterpret_cast<int*>(base + kIdsOff)[buf * CHUNK + slot] = pre_id;
+            bulk_copy_g2s(base + (size_t)buf * kBufBytes + (size_t)slot * kRecBytes, records + (size_t)pre_id * RS,
+                          kRecBytes, bar(buf));
         }
         if (lane == 0) mbar_arrive_expect_tx(bar(buf), (uint32_t)__popc(bits) * kRecBytes);
         __syncwarp();  // ids visible to the whole warp
