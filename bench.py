@@ -275,7 +275,10 @@ def main():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    warmup = max(args.warmup, 3)
+    # Untimed warm-up: at least 25 steps.  Every step allocates ~1.5 GB of outputs / scratch / gradients through torch's
+    # caching allocator exactly like the reference's `_C` functions do; the allocator keeps creating segments
+    # (cudaMalloc, 5-40 ms each, measured with tools/step_jitter.py) for the first ~20 steps of a process.
+    warmup = max(args.warmup, 25)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

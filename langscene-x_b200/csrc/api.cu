@@ -322,7 +322,7 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     pp.focal_x = focal_x; pp.focal_y = focal_y; pp.tan_fovx = a->tanfovx; pp.tan_fovy = a->tanfovy;
     pp.scale_modifier = a->scale_modifier;
     pp.prefiltered = a->prefiltered; pp.render_geo = a->render_geo; pp.include_feature = a->include_feature;
-    pp.rec_stride = rs;
+    pp.rec_stride = rs; pp.n_channels = nch;
     pp.means3D = a->means3D; pp.scales = a->scales; pp.rotations = a->rotations; pp.opacities = a->opacities;
     pp.shs = a->shs; pp.cov3D_precomp = a->cov3D_precomp; pp.colors_precomp = a->colors_precomp;
     pp.language_feature = a->language_feature; pp.language_feature_instance = a->language_feature_instance;

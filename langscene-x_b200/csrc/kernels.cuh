@@ -12,6 +12,7 @@ struct PreprocessFwdParams {
     float focal_x, focal_y, tan_fovx, tan_fovy, scale_modifier;
     int prefiltered, render_geo, include_feature;
     int rec_stride;
+    int n_channels;  // blended channels: 3 + F + Fi + (render_geo ? 5 : 0)
     const float* means3D;
     const float* scales;
     const float* rotations;

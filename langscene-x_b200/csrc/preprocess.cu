@@ -18,6 +18,7 @@
 //     zero-fill traffic at 1M Gaussians.
 //   * arithmetic that feeds radii / tile rects / depth keys keeps the reference's scalar expression
 //     order (including the fp64 island in ndc_to_pix) because those outputs are compared bit-exactly.
+#include "coalesce.cuh"
 #include "kernels.cuh"
 
 namespace lsx {
@@ -104,11 +105,20 @@ __device__ __forceinline__ void ewa_frame(const float3 mean, const float fx, con
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwdParams p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
+constexpr int kPreFwdThreads = 128;
+// smem row stride of the record tile: 16-B aligned rows, and 12 t mod 32 distinct for 8 consecutive t => the
+// row owner's float4 accesses are conflict free
+__host__ __device__ static inline int record_tile_row(int rec_stride) { return rec_stride + 4; }
 
-    // defaults for a culled splat
+// One Gaussian per thread.  `sh_row`: its SH coefficients in shared memory; `rec`: its row of the block's record
+// tile in shared memory, whose feature / map columns have already been filled cooperatively.
+__device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p, const int idx, const float* __restrict__ sh_row,
+                                                   float* __restrict__ rec) {
+    // defaults for a culled splat (its record is never read; keep it finite)
+    reinterpret_cast<float4*>(rec)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(rec)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    rec[REC_HEAD + 0] = rec[REC_HEAD + 1] = rec[REC_HEAD + 2] = 0.f;
+    for (int c = p.n_channels; c < p.rec_stride - REC_HEAD; ++c) rec[REC_HEAD + c] = 0.f;
     p.radii[idx] = 0;
     p.tiles_touched[idx] = 0;
     p.out_observe[idx] = 0;
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwd
         // choice), so the packed colour is reproduced bit for bit.
         const float len = sqrtf(__fmaf_rn(dz0, dz0, __fmaf_rn(dx0, dx0, __fmul_rn(dy0, dy0))));
         const float x = dx0 / len, y = dy0 / len, z = dz0 / len;
-        const float* sh = p.shs + (size_t)idx * p.M * 3;
+        const float* sh = sh_row;
         unsigned clamp_bits = 0;
         // direction polynomials shared by the three colour channels
         float b1y = 0.f, b1z = 0.f, b1x = 0.f, b4 = 0.f, b5 = 0.f, b6 = 0.f, b7 = 0.f, b8 = 0.f;
@@ -246,68 +256,67 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(const PreprocessFwd
     p.conic_opacity[idx] = make_float4(conic.x, conic.y, conic.z, opacity);
     p.tiles_touched[idx] = ntiles;
 
-    // packed blend record (sector aligned): head + channels
-    float* rec = p.records + (size_t)idx * p.rec_stride;
+    // packed blend record (sector aligned): head + colour; the other channels are already in the tile
     reinterpret_cast<float4*>(rec)[0] = make_float4(pix.x, pix.y, conic.x, conic.y);
     reinterpret_cast<float4*>(rec)[1] = make_float4(conic.z, opacity, 0.f, 0.f);
-    float* ch = rec + REC_HEAD;
-    int c = 0;
-    ch[c++] = rgb[0];
-    ch[c++] = rgb[1];
-    ch[c++] = rgb[2];
+    rec[REC_HEAD + 0] = rgb[0];
+    rec[REC_HEAD + 1] = rgb[1];
+    rec[REC_HEAD + 2] = rgb[2];
+}
+
+// Block = 128 Gaussians.  SH coefficients in, and the packed blend records out, move through shared memory with
+// coalesced 16-B accesses (coalesce.cuh); language / instance features and the all_map rows are copied
+// cooperatively straight into their columns of the record tile.
+__global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const PreprocessFwdParams p) {
+    extern __shared__ __align__(16) float s_pre[];
+    const int n_sh = p.M * 3;
+    const int sh_stride = p.shs ? padded_row(n_sh) : 0;  // odd: thread-per-row reads are conflict free
+    const int rec_row = record_tile_row(p.rec_stride);
+    float* s_sh = s_pre;
+    float* s_rec = s_pre + ((kPreFwdThreads * sh_stride + 3) & ~3);
+    const int b0 = blockIdx.x * kPreFwdThreads;
+    const int rows = min(kPreFwdThreads, p.P - b0);
+    if (p.shs && p.colors_precomp == nullptr) slab_load<kPreFwdThreads>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_stride);
+    int c = REC_HEAD + 3;
     if (p.include_feature) {
-        const float* lf = p.language_feature + (size_t)idx * p.F;
-        for (int i = 0; i < p.F; ++i) ch[c++] = lf[i];
-        const float* li = p.language_feature_instance + (size_t)idx * p.Fi;
-        for (int i = 0; i < p.Fi; ++i) ch[c++] = li[i];
+        slab_load<kPreFwdThreads>(s_rec + c, p.language_feature + (size_t)b0 * p.F, rows, p.F, rec_row);
+        c += p.F;
+        slab_load<kPreFwdThreads>(s_rec + c, p.language_feature_instance + (size_t)b0 * p.Fi, rows, p.Fi, rec_row);
+        c += p.Fi;
     }
-    if (p.render_geo) {
-        const float* am = p.all_map + (size_t)idx * 5;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) ch[c++] = am[i];
-    }
-    for (; c < p.rec_stride - REC_HEAD; ++c) ch[c] = 0.f;
+    if (p.render_geo) slab_load<kPreFwdThreads>(s_rec + c, p.all_map + (size_t)b0 * 5, rows, 5, rec_row);
+    __syncthreads();
+    if ((int)threadIdx.x < rows)
+        preprocess_fwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_stride, s_rec + threadIdx.x * rec_row);
+    __syncthreads();
+    slab_store<kPreFwdThreads>(p.records + (size_t)b0 * p.rec_stride, s_rec, rows, p.rec_stride, rec_row);
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward (K8 + K9 fused): dL/dconic, dL/dmean2D, dL/dcolor  ->  dL/d{mean3D, cov3D, sh, scale, rot}
 // ------------------------------------------------------------------------------------------------
-// Unpack one packed gradient record (render_bwd.cu) into the reference's per-tensor layouts; rec == nullptr
-// writes zeros (culled splat).  Record: [rgb(3) | language(F) | instance(Fi) | all_map(5) | pad | 8 geometry terms].
-__device__ __forceinline__ void write_screen_grads(const PreprocessBwdParams& p, const int idx, const float* __restrict__ rec) {
-    const float* geo = rec ? rec + p.n_channels_pad : nullptr;
-    auto at = [&](const float* base, int i) { return base ? base[i] : 0.f; };
-    p.dL_dmean2D[3 * idx + 0] = at(geo, 0);
-    p.dL_dmean2D[3 * idx + 1] = at(geo, 1);
-    p.dL_dmean2D[3 * idx + 2] = 0.f;
-    p.dL_dmean2D_abs[3 * idx + 0] = at(geo, 2);
-    p.dL_dmean2D_abs[3 * idx + 1] = at(geo, 3);
-    p.dL_dmean2D_abs[3 * idx + 2] = 0.f;
-    reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(at(geo, 4), at(geo, 5), 0.f, at(geo, 6));
-    p.dL_dopacity[idx] = at(geo, 7);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) p.dL_dcolor[3 * idx + k] = at(rec, k);
-    int c = 3;
-    if (p.include_feature) {
-        for (int k = 0; k < p.F; ++k) p.dL_dlanguage_feature[(size_t)idx * p.F + k] = at(rec, c + k);
-        c += p.F;
-        for (int k = 0; k < p.Fi; ++k) p.dL_dlanguage_feature_instance[(size_t)idx * p.Fi + k] = at(rec, c + k);
-        c += p.Fi;
-    }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) p.dL_dall_map[5 * idx + k] = p.render_geo ? at(rec, c + k) : 0.f;
-}
+// One Gaussian per thread.  `sh_row` is this Gaussian's SH coefficients in shared memory (read) and is overwritten
+// with dL/dsh at the end; `grec` is its packed gradient record from the tile backward pass (render_bwd.cu):
+// [rgb(3) | language(F) | instance(Fi) | all_map(5) | pad | mean2D.xy, |mean2D|.xy, conic.xyw, opacity].
+// Culled splats have an all-zero record (memset, never accumulated into).
+constexpr int kPreBwdThreads = 128;
 
-__global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwdParams p) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
-
+__device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, float* __restrict__ sh_row,
+                                                   const float* __restrict__ grec) {
     const int n_sh = p.M * 3;
-    float* g_sh = p.dL_dsh ? p.dL_dsh + (size_t)idx * n_sh : nullptr;
+    float* g_sh = p.dL_dsh ? sh_row : nullptr;
+    const float* ggeo = grec + p.n_channels_pad;
+    p.dL_dmean2D[3 * idx + 0] = ggeo[0];
+    p.dL_dmean2D[3 * idx + 1] = ggeo[1];
+    p.dL_dmean2D[3 * idx + 2] = 0.f;
+    p.dL_dmean2D_abs[3 * idx + 0] = ggeo[2];
+    p.dL_dmean2D_abs[3 * idx + 1] = ggeo[3];
+    p.dL_dmean2D_abs[3 * idx + 2] = 0.f;
+    reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(ggeo[4], ggeo[5], 0.f, ggeo[6]);
+    p.dL_dopacity[idx] = ggeo[7];
 
     if (!(p.radii[idx] > 0)) {
         // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
-        write_screen_grads(p, idx, nullptr);
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
 #pragma unroll
@@ -319,10 +328,6 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
             for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
         return;
     }
-
-    const float* grec = p.grad_records + (size_t)idx * p.grad_stride;
-    write_screen_grads(p, idx, grec);
-    const float* ggeo = grec + p.n_channels_pad;  // mean2D.x, mean2D.y, |.|x, |.|y, conic.x, conic.y, conic.w, opacity
 
     const float3 mean = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
     const float* cov6 = (p.cov3D_precomp ? p.cov3D_precomp : p.cov3D) + 6 * (size_t)idx;
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
         const float ox = mean.x - p.campos[0], oy = mean.y - p.campos[1], oz = mean.z - p.campos[2];
         const float len = sqrtf(ox * ox + oy * oy + oz * oz);
         const float x = ox / len, y = oy / len, z = oz / len;
-        const float* sh = p.shs + (size_t)idx * n_sh;
+        const float* sh = sh_row;
         const unsigned cl = p.clamped[idx];
         float gc[3];
 #pragma unroll
@@ -580,6 +585,39 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     }
 }
 
+// Block = 128 Gaussians.  The SH slab and the gradient-record slab of the block are moved through shared memory
+// with coalesced 16-B accesses (coalesce.cuh); dL/dsh and the unpacked colour / feature / map gradients leave the
+// same way.  Every output row is written exactly once (zeros for culled splats).
+__global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const PreprocessBwdParams p) {
+    extern __shared__ __align__(16) float s_pre[];
+    const int n_sh = p.M * 3;
+    const int sh_row = padded_row(n_sh), rec_row = padded_row(p.grad_stride);
+    float* s_sh = s_pre;
+    float* s_rec = s_pre + (p.shs ? kPreBwdThreads * sh_row : 0);
+    const int b0 = blockIdx.x * kPreBwdThreads;
+    const int rows = min(kPreBwdThreads, p.P - b0);
+    if (p.shs) slab_load<kPreBwdThreads>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
+    slab_load<kPreBwdThreads>(s_rec, p.grad_records + (size_t)b0 * p.grad_stride, rows, p.grad_stride, rec_row);
+    __syncthreads();
+    if ((int)threadIdx.x < rows)
+        preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, s_rec + threadIdx.x * rec_row);
+    __syncthreads();
+    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row);
+    slab_store<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, s_rec, rows, 3, rec_row, 0);
+    int c = 3;
+    if (p.include_feature) {
+        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, s_rec, rows, p.F, rec_row, c);
+        c += p.F;
+        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, s_rec, rows, p.Fi, rec_row, c);
+        c += p.Fi;
+    }
+    if (p.render_geo) {
+        slab_store<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, s_rec, rows, 5, rec_row, c);
+    } else {
+        for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
                                                            const float* __restrict__ view, uint8_t* __restrict__ present) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -594,14 +632,29 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 // ------------------------------------------------------------------------------------------------
 int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
-    preprocess_fwd_kernel<<<ceil_div(p.P, 256), 256, 0, stream>>>(p);
+    const int n_sh = p.M * 3;
+    const int sh_stride = p.shs ? padded_row(n_sh) : 0;
+    const size_t smem = ((size_t)((kPreFwdThreads * sh_stride + 3) & ~3) + (size_t)kPreFwdThreads * record_tile_row(p.rec_stride)) *
+                        sizeof(float);
+    static size_t configured = 0;  // benign race: monotone maximum
+    if (smem > configured) {
+        LSX_CUDA_OK(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    preprocess_fwd_kernel<<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
 
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
-    preprocess_bwd_kernel<<<ceil_div(p.P, 256), 256, 0, stream>>>(p);
+    const size_t smem = (size_t)kPreBwdThreads * ((p.shs ? padded_row(p.M * 3) : 0) + padded_row(p.grad_stride)) * sizeof(float);
+    static size_t configured = 0;  // benign race: monotone maximum
+    if (smem > configured) {
+        LSX_CUDA_OK(cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    preprocess_bwd_kernel<<<ceil_div(p.P, kPreBwdThreads), kPreBwdThreads, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
