@@ -161,6 +161,9 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
     const float ddely_dy = 0.5f * (float)p.H;
     const uint32_t w_addr = smem_u32(&s_w[0][0]);
     unsigned parity = 0;
+    float pv[8];          // geometry terms of the last blended entry, not yet reduced across the warp
+    float* pgrec = nullptr;
+    bool pend = false;    // warp-uniform
 
     // round r covers list indices n_eff-1 - (r*CHUNK + lane), i.e. back to front
     auto entry_of = [&](int r) -> long long {
@@ -189,6 +192,13 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             ia += 4;
             const float4 h0 = lds128(ra);
             const float2 h1 = lds64(ra + 16);
+            // Geometry terms of the PREVIOUS blended entry: their shuffle butterfly (5 dependent levels) is issued
+            // here so that its latency overlaps this entry's load -> power -> exp -> alpha chain.
+            if (pend) {
+                WarpTransposeReduce<8, 16>::run(pv, lane);
+                if ((lane & 3u) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), pv[0]);
+                pend = false;
+            }
             const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
             const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
             const float G = expf(power);
@@ -223,15 +233,15 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             const float kdx = ku * dx, kdy = ku * dy;
             const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
             const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
-            float v[8];
-            v[0] = mx;
-            v[1] = my;
-            v[2] = fabsf(mx);
-            v[3] = fabsf(my);
-            v[4] = -0.5f * kdx * dx;
-            v[5] = -0.5f * kdx * dy;
-            v[6] = -0.5f * kdy * dy;
-            v[7] = u;
+            pv[0] = mx;
+            pv[1] = my;
+            pv[2] = fabsf(mx);
+            pv[3] = fabsf(my);
+            pv[4] = -0.5f * kdx * dx;
+            pv[5] = -0.5f * kdx * dy;
+            pv[6] = -0.5f * kdy * dy;
+            pv[7] = u;
+            pend = true;
 
             // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
             const uint32_t wa = w_addr + parity * 128u;
@@ -259,10 +269,12 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
                 const float sum = (cg[ps][0] + cg[ps][1]) + (cg[ps][2] + cg[ps][3]);
                 if (c < p.n_channels && sum != 0.f) atomicAdd(grec + c, sum);
             }
-            // ---- geometry terms: 8 values -> lanes 0,4,...,28 ----
-            WarpTransposeReduce<8, 16>::run(v, lane);
-            if ((lane & 3u) == 0u && v[0] != 0.f) atomicAdd(grec + CT4 + (lane >> 2), v[0]);
+            pgrec = grec;  // the geometry terms (pv) are reduced at the top of the next iteration
         }
+    }
+    if (pend) {
+        WarpTransposeReduce<8, 16>::run(pv, lane);
+        if ((lane & 3u) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), pv[0]);
     }
 }
 
