@@ -3,10 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference|reference-cpu] [--config C3]
 
-A "step" is one forward + backward of ONE 1920x1080 view of the 1M-Gaussian synthetic scene (16-d language
-feature + instance feature + normal/alpha/distance map + plane depth, SH degree 3).  With N > 1 (torchrun)
-every rank renders its own view per step (weak scaling) and the per-Gaussian parameter gradients are summed
-with one NCCL all-reduce of a flat arena inside the timed region.
+A "step" is one optimisation step's gradient on every GPU: forward + backward of `--views-per-gpu` (default 8)
+1920x1080 views of the 1M-Gaussian synthetic scene (16-d language feature + instance feature +
+normal/alpha/distance map + plane depth, SH degree 3), their per-Gaussian parameter gradients summed into one
+flat arena.  With N > 1 (torchrun) every rank renders its own views (weak scaling: 8 views per GPU, i.e. the
+64-view batch of BASELINE config 5 at N = 8) and the arena is summed with ONE NCCL all-reduce inside the timed
+region.  MPix/s = N * views * W * H / time; `ms_per_iter` = time per single-view fwd+bwd (the metric's ms/iter).
 
 Printed JSON (rank 0, one line): see the task contract.  Extras: `stages_ms` (per-stage device times from the
 library's event hooks), `stats` (P_vis, R, S), `peaks` (measured FP32 / EX2 / RED.ADD rates), `ref_cuda`
@@ -33,6 +35,8 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
+NCU_TRAFFIC = {"render_bwd": 608793344, "render_fwd": 370414848}
 
 
 def load_peaks():
@@ -98,7 +102,28 @@ class ClockSampler:
                 "nvml_call_ms_max": round(self.call_ms, 3)}
 
 
+def build_views(cfg_name, device, rank=0, world=1, views=1, seed=0):
+    """The shared scene plus this rank's cameras: global view v = rank*views + i of world*views views on the arc
+    yaw = -15..+15 degrees; a single view overall is the yaw-0 camera."""
+    from lsx_b200.synthetic import CONFIGS, make_all_map, make_camera, make_scene, make_upstream_grads
+    import harness as hz
+    c = CONFIGS[cfg_name]
+    scene = make_scene(c["P"], c["W"], c["H"], F=c["F"], seed=seed, s_med=c["s_med"]).to(device)
+    grads = make_upstream_grads(c["W"], c["H"], c["F"], device=device)
+    bg = torch.zeros(3, device=device)
+    total = world * views
+    out = []
+    for i in range(views):
+        v = rank * views + i
+        yaw = 0.0 if total == 1 else (-15.0 + 30.0 * v / (total - 1))
+        cam = make_camera(c["W"], c["H"], yaw_deg=yaw).to(device)
+        am = make_all_map(scene, cam)
+        out.append({"cam": cam, "am": am, "yaw": yaw, "fargs": hz.native_forward_args(scene, cam, bg, c["F"], all_map=am)})
+    return c, scene, grads, bg, out
+
+
 def build_case(cfg_name, device, view_yaw=0.0, seed=0):
+    """Single-view case (tools/ use this)."""
     from lsx_b200.synthetic import CONFIGS, make_all_map, make_camera, make_scene, make_upstream_grads
     import harness as hz
     c = CONFIGS[cfg_name]
@@ -146,86 +171,115 @@ def time_loop(step_fn, steps, warmup, world, detail=None):
 
 
 def native_stepper(mod, fargs, grads, arena=None, world=1):
-    """Device-resident step: raw `_C`-level forward + backward (+ gradient all-reduce when world > 1)."""
+    """Single-view device-resident step (tools/): raw `_C`-level forward + backward."""
     import harness as hz
-    from lsx_b200.multiview import BWD_TO_GROUP
 
     def step():
         fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
         bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, grads))))
-        if arena is not None:
-            arena.zero_()
+        return fwd, bwd
+    return step
+
+
+def batch_stepper(mod, views, grads, arena, world):
+    """Device-resident step: raw `_C`-level forward + backward of every local view, gradients summed into the
+    flat arena, one all-reduce when world > 1."""
+    import harness as hz
+    from lsx_b200.multiview import BWD_TO_GROUP
+
+    def step():
+        arena.zero_()
+        for vw in views:
+            fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*vw["fargs"])))
+            bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(vw["fargs"], fwd, grads))))
             arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items()})
+        if world > 1:
             arena.all_reduce()
         return fwd, bwd
     return step
 
 
-def e2e_stepper(mod, fargs, grads, cam, pinned, arena=None):
-    """End-to-end step through the operator API with HOST buffers: every step copies this view's camera and its
-    colour supervision gradient from pinned host memory, runs forward + backward, and reads a scalar back."""
+def _pin_views(views, grads):
+    cams = [torch.cat([vw["cam"].viewmatrix.flatten(), vw["cam"].projmatrix.flatten(), vw["cam"].campos.flatten()]).cpu().pin_memory()
+            for vw in views]
+    gcol = grads["color"].cpu().pin_memory()
+    h2d = sum(c.numel() * 4 for c in cams) + len(views) * gcol.numel() * 4
+    return cams, gcol, h2d
+
+
+def e2e_stepper(mod, views, grads, arena, world):
+    """End-to-end step through the reference-shaped `_C` functions with HOST buffers: for every view the camera and
+    its colour-supervision gradient come from pinned host memory, forward + backward run, gradients are summed;
+    one all-reduce when world > 1; two scalars are read back."""
     import harness as hz
+    from lsx_b200.multiview import BWD_TO_GROUP
     dev = grads["color"].device
-    d_cam = torch.empty_like(pinned["cam"], device=dev)
+    cams, gcol, h2d = _pin_views(views, grads)
+    d_cam = torch.empty_like(cams[0], device=dev)
     d_gcol = torch.empty_like(grads["color"])
-    fargs = list(fargs)
     g = dict(grads)
 
     def step():
-        d_cam.copy_(pinned["cam"], non_blocking=True)
-        d_gcol.copy_(pinned["gcol"], non_blocking=True)
-        fargs[11], fargs[12], fargs[19] = d_cam[:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
-        g["color"] = d_gcol
-        fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
-        bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, g))))
-        if arena is not None:
-            from lsx_b200.multiview import BWD_TO_GROUP
-            arena.zero_()
+        arena.zero_()
+        acc = None
+        for vw, cam_h in zip(views, cams):
+            d_cam.copy_(cam_h, non_blocking=True)
+            d_gcol.copy_(gcol, non_blocking=True)
+            fargs = list(vw["fargs"])
+            fargs[11], fargs[12], fargs[19] = d_cam[:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
+            g["color"] = d_gcol
+            fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
+            bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, g))))
             arena.accumulate({gname: bwd[k] for k, gname in BWD_TO_GROUP.items()})
+            acc = fwd["color"].sum() if acc is None else acc + fwd["color"].sum()
+        if world > 1:
             arena.all_reduce()
-        res = torch.stack([fwd["color"].sum(), bwd["means3D"].sum()]).to("cpu", non_blocking=False)
-        return res
-    h2d = pinned["cam"].numel() * 4 + pinned["gcol"].numel() * 4
+        return torch.stack([acc, arena.views["means3D"].sum()]).to("cpu", non_blocking=False)
     return step, h2d, 8
 
 
-def module_e2e_stepper(scene, cam, grads, bg, am, pinned, F, arena=None):
-    """Same as e2e_stepper but through the public nn.Module + autograd (the call a LangScene-X user makes)."""
+def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
+    """Same, through the public nn.Module + autograd (the call a LangScene-X user makes); autograd accumulates the
+    views' gradients in the parameters' .grad, which are then packed into the arena for the all-reduce."""
     from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     dev = scene.means3D.device
-    d_cam = torch.empty_like(pinned["cam"], device=dev)
+    cams, gcol, h2d = _pin_views(views, grads)
+    d_cam = torch.empty_like(cams[0], device=dev)
     d_gcol = torch.empty_like(grads["color"])
     leaf = lambda t: t.detach().clone().requires_grad_(True)
     params = dict(means3D=leaf(scene.means3D), shs=leaf(scene.shs), lang=leaf(scene.language_feature),
                   inst=leaf(scene.instance_feature), opac=leaf(scene.opacities), scales=leaf(scene.scales),
-                  rots=leaf(scene.rotations), am=leaf(am))
+                  rots=leaf(scene.rotations))
+    ams = [leaf(vw["am"]) for vw in views]   # all_map is a per-view derived input (built by the render wrapper)
     m2 = torch.zeros_like(scene.means3D, requires_grad=True)
     m2a = torch.zeros_like(scene.means3D, requires_grad=True)
+    c0 = views[0]["cam"]
 
     def step():
-        d_cam.copy_(pinned["cam"], non_blocking=True)
-        d_gcol.copy_(pinned["gcol"], non_blocking=True)
-        s = GaussianRasterizationSettings(cam.H, cam.W, cam.tanfovx, cam.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
-                                          d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
-        for p in list(params.values()) + [m2, m2a]:
+        for p in list(params.values()) + ams + [m2, m2a]:
             p.grad = None
-        out = GaussianRasterizer(s)(means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"],
-                                    shs=params["shs"], language_feature_precomp=params["lang"],
-                                    language_feature_instance_precomp=params["inst"], scales=params["scales"],
-                                    rotations=params["rots"], all_map=params["am"])
-        color, lf, li, _, _, amap, depth = out
-        torch.autograd.backward([color, lf, li, amap, depth],
-                                [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
-                                 grads["plane_depth"]])
-        if arena is not None:
+        acc = None
+        for am, cam_h in zip(ams, cams):
+            d_cam.copy_(cam_h, non_blocking=True)
+            d_gcol.copy_(gcol, non_blocking=True)
+            s = GaussianRasterizationSettings(c0.H, c0.W, c0.tanfovx, c0.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
+                                              d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
+            out = GaussianRasterizer(s)(means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"],
+                                        shs=params["shs"], language_feature_precomp=params["lang"],
+                                        language_feature_instance_precomp=params["inst"], scales=params["scales"],
+                                        rotations=params["rots"], all_map=am)
+            color, lf, li, _, _, amap, depth = out
+            torch.autograd.backward([color, lf, li, amap, depth],
+                                    [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
+                                     grads["plane_depth"]])
+            acc = color.sum() if acc is None else acc + color.sum()
+        if world > 1:
             arena.zero_()
             arena.accumulate({"means3D": params["means3D"].grad, "sh": params["shs"].grad, "opacity": params["opac"].grad,
                               "scales": params["scales"].grad, "rotations": params["rots"].grad,
-                              "language_feature": params["lang"].grad, "instance_feature": params["inst"].grad,
-                              "all_map": params["am"].grad})
+                              "language_feature": params["lang"].grad, "instance_feature": params["inst"].grad})
             arena.all_reduce()
-        return torch.stack([color.sum(), params["means3D"].grad.sum()]).to("cpu")
-    h2d = pinned["cam"].numel() * 4 + pinned["gcol"].numel() * 4
+        return torch.stack([acc, params["means3D"].grad.sum()]).to("cpu")
     return step, h2d, 8
 
 
@@ -269,28 +323,37 @@ def run_cpu_sample(threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="new", choices=["new", "reference", "reference-cpu"])
     ap.add_argument("--config", default="C3")
+    ap.add_argument("--views-per-gpu", type=int, default=8,
+                    help="views rendered by every GPU per step (8 x 8 GPUs = the 64-view batch of BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    # Untimed warm-up: at least 25 steps.  Every step allocates ~1.5 GB of outputs / scratch / gradients through torch's
-    # caching allocator exactly like the reference's `_C` functions do; the allocator keeps creating segments
-    # (cudaMalloc, 5-40 ms each, measured with tools/step_jitter.py) for the first ~20 steps of a process.
-    warmup = max(args.warmup, 25)
+    V = max(1, args.views_per_gpu)
+    # Untimed warm-up: at least 3 steps and at least 16 single-view passes, so that torch's caching allocator has
+    # created every segment it needs (cudaMalloc costs 5-40 ms) before the timed region starts.
+    warmup = max(args.warmup, 3, -(-16 // V))
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    # stdout carries exactly one JSON line: libraries (e.g. NCCL's version banner) get stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     if args.impl == "reference-cpu":
         if rank == 0:
             cb = run_cpu_sample()
-            print(json.dumps({"impl": "reference-cpu", "metric": METRIC, "value": cb["value"], "unit": "MPix/s",
-                              "n_gpus": 0, "steps": 1, "warmup": 1, "higher_is_better": True, "cpu_baseline": cb,
-                              "e2e": {"value": cb["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0,
-                                      "d2h_bytes_per_step": 0}}))
+            emit({"impl": "reference-cpu", "metric": METRIC, "value": cb["value"], "unit": "MPix/s",
+                  "n_gpus": 0, "steps": 1, "warmup": 1, "higher_is_better": True, "cpu_baseline": cb,
+                  "e2e": {"value": cb["value"], "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     torch.cuda.set_device(local_rank)
@@ -304,64 +367,67 @@ def main():
     from lsx_b200.multiview import GradArena
 
     hbm_peak, peak_src, peaks_json = load_peaks()
-    # every rank renders its own view of the shared scene (yaw spread like the multi-view generator)
-    yaw = 0.0 if world == 1 else (-15.0 + 30.0 * rank / (world - 1))
-    c, scene, cam, grads, bg, am, fargs = build_case(args.config, device, view_yaw=yaw)
+    c, scene, grads, bg, views = build_views(args.config, device, rank, world, V)
     P, W, H, F = c["P"], c["W"], c["H"], c["F"]
     M, Fi = 16, 3
+    Ct = 3 + F + Fi + 5
 
     if args.impl == "reference":
         mod = hz.ref_rast_for(F)
         if mod is None:
             if rank == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/*.so not built (reference tree was not mounted at build time)"}))
+                emit({"impl": "reference", "unavailable": "oracle/_ref/*.so not built (reference tree was not mounted at build time)"})
             return
     else:
         mod = ops
-    arena = GradArena.allocate(P, M, F, Fi, device) if world > 1 else None
+    arena = GradArena.allocate(P, M, F, Fi, device)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # runs through both timed regions
-    # ---- device-resident timing ----------------------------------------------------------------------
-    step = native_stepper(mod, fargs, grads, arena, world)
-    fwd, bwd = step()
-    torch.cuda.synchronize()
-    R = int(fwd["num_rendered"])
-    P_vis = int((fwd["radii"] > 0).sum())
-    if args.impl == "new":
-        nbuf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H, 3 + F + Fi + 5)
-    else:
-        nbuf = hz.parse_ref_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H)
-    S = int(nbuf["n_contrib"].long().sum())
-    del nbuf, fwd, bwd
+    # ---- per-view statistics (untimed) ------------------------------------------------------------------
+    stats_views = []
+    for i, vw in enumerate(views):
+        fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*vw["fargs"])))
+        torch.cuda.synchronize()
+        st = {"yaw": round(vw["yaw"], 3), "R": int(fwd["num_rendered"]), "P_vis": int((fwd["radii"] > 0).sum())}
+        if i == 0:
+            if args.impl == "new":
+                nbuf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, st["R"], W, H, Ct)
+            else:
+                nbuf = hz.parse_ref_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, st["R"], W, H)
+            st["S"] = int(nbuf["n_contrib"].long().sum())
+            del nbuf
+        stats_views.append(st)
+        del fwd
+    R, P_vis, S = stats_views[0]["R"], stats_views[0]["P_vis"], stats_views[0]["S"]
 
+    # ---- device-resident timing ----------------------------------------------------------------------
+    step = batch_stepper(mod, views, grads, arena, world)
     launches0 = _lib.kernel_launch_count()
     step_detail = {}
     ms_total = time_loop(step, args.steps, warmup, world, step_detail)
     launches = (_lib.kernel_launch_count() - launches0) if args.impl == "new" else 0
     ms_step = ms_total / args.steps
-    mpix = world * W * H / (ms_step * 1e-3) / 1e6
+    mpix = world * V * W * H / (ms_step * 1e-3) / 1e6
 
     # ---- per-stage device times (separate short run so the event hooks do not touch the headline number) ----
     stages = {}
     if args.impl == "new":
         _lib.profile_enable(True)
-        for _ in range(5):
+        for _ in range(2):
             step()
         torch.cuda.synchronize()
-        stages = {k: v / 5 for k, v in _lib.profile_read().items() if v > 0}
+        stages = {k: v / (2 * V) for k, v in _lib.profile_read().items() if v > 0}   # ms per view
         _lib.profile_enable(False)
 
-    # ---- end-to-end through the public module API with host buffers ------------------------------------------
-    pinned = {"cam": torch.cat([cam.viewmatrix.flatten(), cam.projmatrix.flatten(), cam.campos.flatten()]).cpu().pin_memory(),
-              "gcol": grads["color"].cpu().pin_memory()}
+    # ---- end-to-end through the public API with host buffers ---------------------------------------------------
     if args.impl == "new":
-        estep, h2d, d2h = module_e2e_stepper(scene, cam, grads, bg, am, pinned, F, arena)
+        estep, h2d, d2h = module_e2e_stepper(scene, views, grads, bg, F, arena, world)
     else:
-        estep, h2d, d2h = e2e_stepper(mod, fargs, grads, cam, pinned, arena)
-    ms_e2e = time_loop(estep, args.steps, warmup, world) / args.steps
+        estep, h2d, d2h = e2e_stepper(mod, views, grads, arena, world)
+    ms_e2e = time_loop(estep, args.steps, max(3, warmup // 2), world) / args.steps
     clocks = sampler.stop() if sampler else None
-    e2e = {"value": world * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    e2e = {"value": world * V * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
+           "ms_per_iter": ms_e2e / V, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if args.impl == "new"
                   else "reference _C.rasterize_gaussians/_backward (pybind)"}
 
@@ -370,47 +436,56 @@ def main():
             dist.destroy_process_group()
         return
 
-    fwd_b, bwd_b = algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi)
-    Ct = 3 + F + Fi + 5
+    fwd_b = bwd_b = 0
+    for st in stats_views:
+        fb, bb = algorithmic_bytes(P, st["P_vis"], st["R"], W, H, M, F, Fi)
+        fwd_b, bwd_b = fwd_b + fb, bwd_b + bb
     out = {
         "metric": METRIC, "value": mpix, "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-        "ms_per_step": ms_step, "ms_per_step_median": step_detail.get("median_ms"), "ms_per_step_max": step_detail.get("max_ms"),
+        "ms_per_step": ms_step, "ms_per_iter": ms_step / V, "ms_per_step_median": step_detail.get("median_ms"),
+        "ms_per_step_max": step_detail.get("max_ms"),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "impl": args.impl,
         "config": {"workload": f"{args.config}: {P} Gaussians, {W}x{H}, SH degree 3, F={F} language + {Fi} instance + 5 map "
-                               f"channels + plane depth, 1 view per GPU per step, fwd+bwd"
-                               + (", + NCCL all-reduce of the flat parameter-gradient arena" if world > 1 else ""),
-                   "l2": "per-step working set (~1.6 GB of inputs, records, lists, images, gradients) exceeds the 126 MB L2; no flush needed",
+                               f"channels + plane depth; one step = fwd+bwd of {V} views per GPU ({world * V} views in all, "
+                               f"yaw -15..15 deg), gradients summed into one flat arena"
+                               + (", + ONE NCCL all-reduce of the arena" if world > 1 else ""),
+                   "views_per_gpu": V, "ms_per_iter_is": "ms_per_step / views_per_gpu = one single-view fwd+bwd (BASELINE's ms/iter)",
+                   "l2": "per-view working set (~1.6 GB of inputs, records, lists, images, gradients) exceeds the 126 MB L2; no flush needed",
                    "upstream_grads": "fixed N(0,1)/(W*H) tensors, no loss inside the timed region"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "stats": {"P_vis": P_vis, "R": R, "S": S, "Ct": Ct},
+        "stats": {"P_vis": P_vis, "R": R, "S": S, "Ct": Ct, "per_view": stats_views},
         "stages_ms": stages,
     }
-    # roofline of the dominant kernel (live stage times)
+    # roofline of the dominant kernel (live stage times, per launch = per view; view 0's sizes)
     if stages:
         dom = max(("render_fwd", "render_bwd"), key=lambda k: stages.get(k, 0.0))
-        rec = R * (28 + 4 * Ct)
-        kbytes = rec + W * H * 4 * (Ct + 1 + 2) if dom == "render_fwd" else rec + W * H * 4 * ((Ct + 1) + 5 + 2) + P_vis * 4 * (Ct + 8)
+        Rm = sum(st["R"] for st in stats_views) / len(stats_views)
+        Pm = sum(st["P_vis"] for st in stats_views) / len(stats_views)
+        rec = Rm * (28 + 4 * Ct)
+        kbytes = rec + W * H * 4 * (Ct + 1 + 2) if dom == "render_fwd" else rec + W * H * 4 * ((Ct + 1) + 5 + 2) + Pm * 4 * (Ct + 8)
         ach = kbytes / (stages[dom] * 1e-3) / 1e9
         out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src,
-                           "note": "the render kernels are FP32/shuffle-issue bound, not HBM bound (see `fp32` and DESIGN.md); "
-                                   "algorithmic bytes = R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd)"}
+                           "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                           "launch_ms": stages[dom],
+                           "note": "the render kernels are FP32 instruction-issue bound, not HBM bound (DESIGN.md 3, profiles/): "
+                                   "algorithmic bytes per launch = R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd), "
+                                   "means over this rank's views; `traffic` = dram bytes of one ncu --set full capture of view 0"}
         it_bytes = fwd_b + bwd_b
         out["roofline_iteration"] = {"bound": "hbm", "algorithmic_bytes": it_bytes,
                                      "achieved": it_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                      "frac": it_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak}
         try:
+            import ctypes
             scratch = torch.empty(64 << 20, dtype=torch.uint8, device=device)
             res = {}
             for kind, name in ((0, "fp32_ffma_tflops"), (1, "mufu_ex2_gops"), (2, "red_add_f32_gops")):
-                import ctypes
                 val = ctypes.c_double(0)
                 _lib.check(_lib.load().lsx_microbench(kind, scratch.data_ptr(), scratch.numel(), ctypes.byref(val),
                                                       torch.cuda.current_stream().cuda_stream), "microbench")
                 res[name] = val.value
             out["peaks"] = res
-            # flops model of SURVEY.md §8d with B unknown: lower bound from the per-test work only
+            # flops model of SURVEY.md 8d with B unknown: lower bound from the per-test work only
             out["fp32"] = {"tests_S": S, "flops_lower_bound": 14 * S + 16 * S,
                            "achieved_tflops_lower_bound": (30 * S) / ((stages["render_fwd"] + stages["render_bwd"]) * 1e-3) / 1e12,
                            "peak_tflops": res["fp32_ffma_tflops"]}
@@ -419,10 +494,11 @@ def main():
     if args.impl == "new" and world == 1:
         ref = hz.ref_rast_for(F)
         if ref is not None:
-            rstep = native_stepper(ref, fargs, grads)
-            rms = time_loop(rstep, max(5, args.steps // 2), 3, 1) / max(5, args.steps // 2)
-            out["ref_cuda"] = {"ms_per_step": rms, "value": W * H / (rms * 1e-3) / 1e6, "unit": "MPix/s",
-                               "what": "reference CUDA rasterizer (oracle/_ref/ref_rast_f16.so, sm_100a recompile), same inputs, same process",
+            rstep = batch_stepper(ref, views, grads, arena, 1)
+            rsteps = max(2, args.steps // 4)
+            rms = time_loop(rstep, rsteps, 1, 1) / rsteps
+            out["ref_cuda"] = {"ms_per_step": rms, "ms_per_iter": rms / V, "value": V * W * H / (rms * 1e-3) / 1e6, "unit": "MPix/s",
+                               "what": "reference CUDA rasterizer (oracle/_ref/ref_rast_f16.so, sm_100a recompile), same step, same process",
                                "speedup_device_resident": rms / ms_step}
         if not args.no_cpu_baseline:
             try:
@@ -431,10 +507,10 @@ def main():
                 out["cpu_baseline"] = {"value": None, "unit": "MPix/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if args.impl == "reference":
         out["cpu_baseline"] = {"value": out["value"], "unit": "MPix/s", "cores": 0, "kind": "reference",
-                               "sample": "this arm runs the reference's CUDA implementation (unmodified sources recompiled for "
-                                         "sm_100a) on the GPU — the reference has no CPU implementation of this path; the CPU "
-                                         "restatement is available with --impl reference-cpu"}
-    print(json.dumps(out))
+                               "sample": "this arm runs the reference's own implementation of the path — its CUDA rasterizer, unmodified "
+                                         "sources recompiled for sm_100a (oracle/_ref) — on the GPU; the reference has no CPU "
+                                         "implementation of this path.  The CPU restatement is timed by --impl reference-cpu"}
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -39,17 +39,27 @@ def _prep(t, name, device):
 
 
 class _ScratchAlloc:
-    """The resizeFunctional analogue (rasterize_points.cu:27-33): torch owns the scratch bytes."""
+    """The resizeFunctional analogue (rasterize_points.cu:27-33): torch owns the scratch bytes.
+
+    The ctypes callback must not capture `self`: self -> fn -> closure -> self would be a reference cycle, and the
+    scratch tensor (hundreds of MB) would then survive until CPython's cyclic collector runs instead of being
+    released by reference counting when the caller drops it."""
 
     def __init__(self, device):
-        self.device = device
-        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        holder = []
 
         def _cb(_user, nbytes):
-            self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-            return self.tensor.data_ptr()
+            t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            holder[:] = [t]
+            return t.data_ptr()
 
+        self._holder = holder
+        self._device = device
         self.fn = _lib.ALLOC_FN(_cb)
+
+    @property
+    def tensor(self):
+        return self._holder[0] if self._holder else torch.empty(0, dtype=torch.uint8, device=self._device)
 
 
 def _stream_handle(device):

@@ -317,6 +317,29 @@ def test_two_forwards_outstanding_and_side_stream():
     assert hz.rel_err(dbg["means3D"], refA["means3D"]) < 1e-5
 
 
+def test_no_memory_growth_without_cyclic_gc():
+    """Scratch, outputs and gradients must be released by reference counting alone (a ctypes callback capturing its
+    owner once kept every call's ~400 B/Gaussian scratch alive until the cyclic collector ran)."""
+    import gc
+    ops = _new()
+    scene, cam, grads = _scene(50_000, 320, 240, 3, seed=11)
+    fargs = hz.native_forward_args(scene, cam, torch.zeros(3, device="cuda:0"), 3)
+    hz.run_native(ops, fargs, grads)
+    torch.cuda.synchronize()
+    gc.collect()
+    gc.disable()
+    try:
+        base = torch.cuda.memory_allocated()
+        for _ in range(6):
+            fwd, bwd = hz.run_native(ops, fargs, grads)
+            del fwd, bwd
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    assert grown < (1 << 20), f"{grown} bytes still allocated after 6 forward/backward calls"
+
+
 def test_headline_size_properties():
     """BASELINE config 3 (1M Gaussians, 1080p, 16-d feature): size-independent properties + reference if built."""
     P, W, H, F = 1_000_000, 1920, 1080, 16

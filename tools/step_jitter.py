@@ -1,4 +1,4 @@
-"""Diagnostic: per-step wall/device times of the raw native step loop, to locate sporadic long steps."""
+"""Diagnostic: per-step device times and allocator activity of bench.py's batch step, to locate sporadic long steps."""
 import gc
 import os
 import sys
@@ -11,33 +11,28 @@ for p in (os.path.join(REPO, "langscene-x_b200"), REPO, os.path.join(REPO, "test
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-import harness as hz  # noqa: E402
 from lsx_b200 import ops  # noqa: E402
+from lsx_b200.multiview import GradArena  # noqa: E402
 
 dev = torch.device("cuda:0")
-c, scene, cam, grads, bg, am, fargs = bench.build_case("C3", dev)
-step = bench.native_stepper(ops, fargs, grads)
-sampler = None
-for rep in range(6):
-    if rep == 3:
-        sampler = bench.ClockSampler(0)
-        print('sampler started')
-    gc.collect()
-    if rep == 2:
-        gc.disable()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(41)]
-    wall = []
+V = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+c, scene, grads, bg, views = bench.build_views("C3", dev, 0, 1, V)
+arena = GradArena.allocate(c["P"], 16, c["F"], 3, dev)
+step = bench.batch_stepper(ops, views, grads, arena, 1)
+gc.collect()
+gc.disable()
+for rep in range(2):
+    n = 16
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    allocs, reserved = [], []
     ev[0].record()
-    for i in range(40):
-        t0 = time.perf_counter()
+    for i in range(n):
         step()
-        wall.append((time.perf_counter() - t0) * 1e3)
         ev[i + 1].record()
+        st = torch.cuda.memory_stats()
+        allocs.append(st.get("num_device_alloc", 0))
+        reserved.append(st.get("reserved_bytes.all.current", 0) / 1e9)
     torch.cuda.synchronize()
-    devms = [ev[i].elapsed_time(ev[i + 1]) for i in range(40)]
-    print("rep", rep, "device ms:", " ".join(f"{x:.1f}" for x in devms))
-    print("rep", rep, "wall   ms:", " ".join(f"{x:.1f}" for x in wall))
-    print("mem reserved GB", torch.cuda.memory_reserved() / 1e9, "num_alloc_retries", torch.cuda.memory_stats().get("num_alloc_retries"),
-          "segments", torch.cuda.memory_stats().get("segment.all.allocated"))
-
-if sampler: print(sampler.stop())
+    print("rep", rep, "ms/view:", " ".join(f"{ev[i].elapsed_time(ev[i + 1]) / V:.2f}" for i in range(n)))
+    print("   cudaMalloc calls (cumulative):", allocs)
+    print("   reserved GB:", " ".join(f"{r:.1f}" for r in reserved))
