@@ -114,13 +114,14 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
             if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
             if (blend) {
                 const float w = alpha * T;
+                float4 f[CT4 / 4];
+                lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
 #pragma unroll
                 for (int q = 0; q < CT4 / 4; ++q) {
-                    const float4 f = lds128(ra + REC_HEAD * 4 + q * 16);
-                    acc[4 * q + 0] += f.x * w;
-                    acc[4 * q + 1] += f.y * w;
-                    acc[4 * q + 2] += f.z * w;
-                    acc[4 * q + 3] += f.w * w;
+                    acc[4 * q + 0] += f[q].x * w;
+                    acc[4 * q + 1] += f[q].y * w;
+                    acc[4 * q + 2] += f[q].z * w;
+                    acc[4 * q + 3] += f[q].w * w;
                 }
                 T = test_T;
                 last_contributor = (uint32_t)(r * CHUNK + pos + 1);

@@ -18,6 +18,48 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
+// N consecutive 16-B shared loads issued back to back from ONE asm block, so that their latencies overlap
+// (separate volatile asm statements are kept in program order with their consumers in between).
+template <int N>
+__device__ __forceinline__ void lds128xN(uint32_t addr, float4* f) {
+    static_assert(N >= 1 && N <= 4, "group size");
+    if constexpr (N == 1) {
+        f[0] = lds128(addr);
+    } else if constexpr (N == 2) {
+        asm volatile(
+            "ld.shared.v4.f32 {%0, %1, %2, %3}, [%8];\n\t"
+            "ld.shared.v4.f32 {%4, %5, %6, %7}, [%8+16];"
+            : "=f"(f[0].x), "=f"(f[0].y), "=f"(f[0].z), "=f"(f[0].w), "=f"(f[1].x), "=f"(f[1].y), "=f"(f[1].z), "=f"(f[1].w)
+            : "r"(addr)
+            : "memory");
+    } else if constexpr (N == 3) {
+        asm volatile(
+            "ld.shared.v4.f32 {%0, %1, %2, %3}, [%12];\n\t"
+            "ld.shared.v4.f32 {%4, %5, %6, %7}, [%12+16];\n\t"
+            "ld.shared.v4.f32 {%8, %9, %10, %11}, [%12+32];"
+            : "=f"(f[0].x), "=f"(f[0].y), "=f"(f[0].z), "=f"(f[0].w), "=f"(f[1].x), "=f"(f[1].y), "=f"(f[1].z), "=f"(f[1].w),
+              "=f"(f[2].x), "=f"(f[2].y), "=f"(f[2].z), "=f"(f[2].w)
+            : "r"(addr)
+            : "memory");
+    } else {
+        asm volatile(
+            "ld.shared.v4.f32 {%0, %1, %2, %3}, [%16];\n\t"
+            "ld.shared.v4.f32 {%4, %5, %6, %7}, [%16+16];\n\t"
+            "ld.shared.v4.f32 {%8, %9, %10, %11}, [%16+32];\n\t"
+            "ld.shared.v4.f32 {%12, %13, %14, %15}, [%16+48];"
+            : "=f"(f[0].x), "=f"(f[0].y), "=f"(f[0].z), "=f"(f[0].w), "=f"(f[1].x), "=f"(f[1].y), "=f"(f[1].z), "=f"(f[1].w),
+              "=f"(f[2].x), "=f"(f[2].y), "=f"(f[2].z), "=f"(f[2].w), "=f"(f[3].x), "=f"(f[3].y), "=f"(f[3].z), "=f"(f[3].w)
+            : "r"(addr)
+            : "memory");
+    }
+}
+// all NQ float4 of a row, in groups of GROUP loads
+template <int NQ, int GROUP = 4>
+__device__ __forceinline__ void lds_row(uint32_t addr, float4* f) {
+#pragma unroll
+    for (int q = 0; q + GROUP <= NQ; q += GROUP) lds128xN<GROUP>(addr + q * 16, f + q);
+    if constexpr (NQ % GROUP != 0) lds128xN<NQ % GROUP>(addr + (NQ / GROUP) * GROUP * 16, f + (NQ / GROUP) * GROUP);
+}
 __device__ __forceinline__ float2 lds64(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
