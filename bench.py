@@ -207,45 +207,75 @@ def _pin_views(views, grads):
     return cams, gcol, h2d
 
 
+class HostFeeder:
+    """Per-view host inputs (camera matrices + colour-supervision gradient) in pinned memory, copied to the device on
+    a side stream into two alternating buffers, so that the copy of view i+1 overlaps the compute of view i.  The
+    first view of every step is copied inside the step without overlap; all copies are inside the timed region."""
+
+    def __init__(self, views, grads):
+        dev = grads["color"].device
+        self.cams, self.gcol, self.h2d_bytes = _pin_views(views, grads)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.buf = [(torch.empty_like(self.cams[0], device=dev), torch.empty_like(grads["color"])) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        for e in self.free:
+            e.record()
+
+    def fetch(self, i):
+        """enqueue the copy of view i into buffer i & 1 (after the compute that last used it)"""
+        slot = i & 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(self.free[slot])
+            self.buf[slot][0].copy_(self.cams[i], non_blocking=True)
+            self.buf[slot][1].copy_(self.gcol, non_blocking=True)
+            self.ready[slot].record(self.stream)
+
+    def get(self, i):
+        slot = i & 1
+        torch.cuda.current_stream().wait_event(self.ready[slot])
+        return self.buf[slot]
+
+    def release(self, i):
+        self.free[i & 1].record()
+
+
 def e2e_stepper(mod, views, grads, arena, world):
     """End-to-end step through the reference-shaped `_C` functions with HOST buffers: for every view the camera and
     its colour-supervision gradient come from pinned host memory, forward + backward run, gradients are summed;
     one all-reduce when world > 1; two scalars are read back."""
     import harness as hz
     from lsx_b200.multiview import BWD_TO_GROUP
-    dev = grads["color"].device
-    cams, gcol, h2d = _pin_views(views, grads)
-    d_cam = torch.empty_like(cams[0], device=dev)
-    d_gcol = torch.empty_like(grads["color"])
+    feeder = HostFeeder(views, grads)
     g = dict(grads)
 
     def step():
         arena.zero_()
         acc = None
-        for vw, cam_h in zip(views, cams):
-            d_cam.copy_(cam_h, non_blocking=True)
-            d_gcol.copy_(gcol, non_blocking=True)
+        feeder.fetch(0)
+        for i, vw in enumerate(views):
+            if i + 1 < len(views):
+                feeder.fetch(i + 1)
+            d_cam, d_gcol = feeder.get(i)
             fargs = list(vw["fargs"])
             fargs[11], fargs[12], fargs[19] = d_cam[:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
             g["color"] = d_gcol
             fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
             bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, g))))
+            feeder.release(i)
             arena.accumulate({gname: bwd[k] for k, gname in BWD_TO_GROUP.items()})
             acc = fwd["color"].sum() if acc is None else acc + fwd["color"].sum()
         if world > 1:
             arena.all_reduce()
         return torch.stack([acc, arena.views["means3D"].sum()]).to("cpu", non_blocking=False)
-    return step, h2d, 8
+    return step, feeder.h2d_bytes, 8
 
 
 def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
     """Same, through the public nn.Module + autograd (the call a LangScene-X user makes); autograd accumulates the
     views' gradients in the parameters' .grad, which are then packed into the arena for the all-reduce."""
     from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
-    dev = scene.means3D.device
-    cams, gcol, h2d = _pin_views(views, grads)
-    d_cam = torch.empty_like(cams[0], device=dev)
-    d_gcol = torch.empty_like(grads["color"])
+    feeder = HostFeeder(views, grads)
     leaf = lambda t: t.detach().clone().requires_grad_(True)
     params = dict(means3D=leaf(scene.means3D), shs=leaf(scene.shs), lang=leaf(scene.language_feature),
                   inst=leaf(scene.instance_feature), opac=leaf(scene.opacities), scales=leaf(scene.scales),
@@ -259,9 +289,11 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
         for p in list(params.values()) + ams + [m2, m2a]:
             p.grad = None
         acc = None
-        for am, cam_h in zip(ams, cams):
-            d_cam.copy_(cam_h, non_blocking=True)
-            d_gcol.copy_(gcol, non_blocking=True)
+        feeder.fetch(0)
+        for i, am in enumerate(ams):
+            if i + 1 < len(ams):
+                feeder.fetch(i + 1)
+            d_cam, d_gcol = feeder.get(i)
             s = GaussianRasterizationSettings(c0.H, c0.W, c0.tanfovx, c0.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
                                               d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
             out = GaussianRasterizer(s)(means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"],
@@ -272,6 +304,7 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
             torch.autograd.backward([color, lf, li, amap, depth],
                                     [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
                                      grads["plane_depth"]])
+            feeder.release(i)
             acc = color.sum() if acc is None else acc + color.sum()
         if world > 1:
             arena.zero_()
@@ -280,7 +313,7 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
                               "language_feature": params["lang"].grad, "instance_feature": params["inst"].grad})
             arena.all_reduce()
         return torch.stack([acc, params["means3D"].grad.sum()]).to("cpu")
-    return step, h2d, 8
+    return step, feeder.h2d_bytes, 8
 
 
 def algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi):
