@@ -39,7 +39,7 @@ def _bit_equal(a, b):
     return bool((a.contiguous().view(torch.int32) == b.contiguous().view(torch.int32)).all())
 
 
-def _compare_all(fargs, grads, F, P, W, H, n_blend, bwd_tol=BWD_TOL):
+def _compare_all(fargs, grads, F, P, W, H, n_blend, bwd_tol=BWD_TOL, depth_tol=FWD_TOL, check_grads=True):
     ref = hz.ref_rast_for(F)
     if ref is None:
         pytest.skip("oracle/_ref not built")
@@ -66,7 +66,7 @@ def _compare_all(fargs, grads, F, P, W, H, n_blend, bwd_tol=BWD_TOL):
     # ---- forward images ---------------------------------------------------------------------------------
     for k in ["color", "language_feature", "instance_feature", "all_map", "plane_depth"]:
         if rf[k].numel() > 1 and float(rf[k].abs().max()) > 0:
-            assert hz.rel_err(nf[k], rf[k]) < FWD_TOL, k
+            assert hz.rel_err(nf[k], rf[k]) < (depth_tol if k == "plane_depth" else FWD_TOL), k
         else:
             assert nf[k].shape == rf[k].shape and float(nf[k].abs().max()) == 0.0, k
     # ---- gradients -------------------------------------------------------------------------------------------
@@ -74,6 +74,8 @@ def _compare_all(fargs, grads, F, P, W, H, n_blend, bwd_tol=BWD_TOL):
     # conic -> covariance -> scale/rotation chain amplifies that noise (cancellations in backward.cu:210-212,333-336).
     # Bound: max(1e-4, 6 x the reference's own run-to-run spread over 5 runs) per tensor  (SURVEY.md Appendix B);
     # the spread of a handful of runs underestimates the tail of the max-over-elements statistic it is compared with.
+    if not check_grads:
+        return rf, nf
     reruns = [dict(zip(hz.BWD_NAMES, ref.rasterize_gaussians_backward(*hz.native_backward_args(fargs, rf, grads))))
               for _ in range(4)]
     for k in hz.BWD_NAMES:
@@ -315,6 +317,31 @@ def test_two_forwards_outstanding_and_side_stream():
     fa_dbg[22] = True  # debug: synchronise + check after every stage
     dbg = hz.run_native(ops, fa_dbg, gA)[1]
     assert hz.rel_err(dbg["means3D"], refA["means3D"]) < 1e-5
+
+
+@pytest.mark.parametrize("s_med,aniso,opac_shift,seed", [
+    (0.02, 2.0, 0.0, 21),     # large, strongly anisotropic splats (needle-like footprints cut across many blocks)
+    (0.004, 1.5, -4.0, 22),   # mostly near-transparent splats: opacity close to the 1/255 threshold
+    (0.08, 0.3, 2.0, 23),     # huge opaque splats: early termination everywhere
+])
+def test_footprint_culling_is_conservative(s_med, aniso, opac_shift, seed):
+    """The sub-tile footprint masks (cull.cu) may only skip (block, entry) pairs the reference would `continue` on.
+    Any false cull changes n_contrib / final_T / out_observe, which are compared bit for bit here on scenes built to
+    stress the mask test: needles, opacities at the alpha threshold, splats far larger than a tile."""
+    P, W, H, F = 20_000, 272, 208, 3
+    scene, cam, grads = _scene(P, W, H, F, seed=seed, s_med=s_med)
+    g = torch.Generator().manual_seed(seed)
+    scene.scales = (scene.scales * torch.exp(aniso * torch.randn(P, 3, generator=g)).to(scene.scales.device)).contiguous()
+    scene.opacities = torch.sigmoid(torch.logit(scene.opacities.clamp(1e-4, 1 - 1e-4)) + opac_shift).contiguous()
+    fargs = hz.native_forward_args(scene, cam, torch.tensor([0.2, 0.1, 0.4], device="cuda:0"), F)
+    # plane depth = A4 / -(A0 rx + A1 ry + A2 + 1e-8) is a ratio of two accumulated sums; where almost nothing is opaque
+    # both are ~1e-3 and the last-bit difference of  f * (alpha T)  (here) vs  (f alpha) T  (forward.cu:388-392) is
+    # amplified — the accumulated maps themselves still agree to 1e-5.
+    # Gradients are compared except in the near-transparent scene: there dL/dplane_depth is folded into the map
+    # gradient through 1/tmp and 1/tmp^2 with tmp = <n, ray> ~ 1e-3 (backward.cu:497-503), which turns both
+    # implementations' gradients into amplified rounding noise; the culling claim is carried by the bit-exact tier.
+    _compare_all(fargs, grads, F, P, W, H, 3 + F + 3 + 5, depth_tol=1e-4 if opac_shift < 0 else FWD_TOL,
+                 check_grads=opac_shift >= 0)
 
 
 def test_no_memory_growth_without_cyclic_gc():
