@@ -187,12 +187,19 @@ def batch_stepper(mod, views, grads, arena, world):
     import harness as hz
     from lsx_b200.multiview import BWD_TO_GROUP
 
+    fused = hasattr(mod, "distCUDA2")  # lsx_b200.ops: its backward accumulates straight into the arena
+
     def step():
         arena.zero_()
         for vw in views:
             fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*vw["fargs"])))
-            bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(vw["fargs"], fwd, grads))))
-            arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items()})
+            bargs = hz.native_backward_args(vw["fargs"], fwd, grads)
+            if fused:
+                bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*bargs, grad_buffers=arena.grad_buffers(),
+                                                                              accumulate=True)))
+            else:
+                bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*bargs)))
+                arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items()})
         if world > 1:
             arena.all_reduce()
         return fwd, bwd

@@ -43,7 +43,7 @@ extern "C" {
 #define LSX_API
 #endif
 
-#define LSX_ABI_VERSION 1
+#define LSX_ABI_VERSION 2
 #define LSX_MAX_BLEND_CHANNELS 40 /* 3 + F + Fi + 5 must not exceed this */
 
 /* scratch allocation callback: must return a device pointer to at least `bytes` bytes, aligned to
@@ -144,6 +144,12 @@ typedef struct lsx_backward_args {
     float* dL_drotations;    /* P*4 */
     float* dL_dall_map;      /* P*5 */
     void* stream;
+    /* Multi-view gradient accumulation (no reference counterpart: the reference returns fresh tensors and lets autograd add
+     * them).  When non-zero, the PARAMETER gradients — dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations,
+     * dL_dcolors, dL_dlanguage_feature(_instance), dL_dall_map, dL_dcov3D — are added to the buffers' current contents
+     * (which must then be initialised) instead of overwriting them; the per-view screen-space outputs dL_dmeans2D,
+     * dL_dmeans2D_abs and dL_dconic are always overwritten. */
+    int32_t accumulate_param_grads;
 } lsx_backward_args;
 
 LSX_API int lsx_rasterize_backward(const lsx_backward_args* args);

@@ -58,10 +58,11 @@ __device__ __forceinline__ void slab_load(float* __restrict__ s, const float* __
     }
 }
 
-// smem (row stride srow, columns [col0, col0 + rowf)) -> global (rows x rowf, contiguous)
+// smem (row stride srow, columns [col0, col0 + rowf)) -> global (rows x rowf, contiguous);
+// accumulate: g += s instead of g = s
 template <int NT>
 __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* __restrict__ s, int rows, int rowf, int srow,
-                                           int col0 = 0) {
+                                           int col0 = 0, bool accumulate = false) {
     const int total = rows * rowf;
     const int tid = threadIdx.x;
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0 && rowf >= 4) {
@@ -81,6 +82,13 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
                 }
                 vv[k] = s[rk * srow + col0 + ck];
             }
+            if (accumulate) {
+                const float4 o = reinterpret_cast<const float4*>(g)[i];
+                vv[0] += o.x;
+                vv[1] += o.y;
+                vv[2] += o.z;
+                vv[3] += o.w;
+            }
             reinterpret_cast<float4*>(g)[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
             r += dq;
             c += dr;
@@ -91,12 +99,14 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
         }
         for (int e2 = (n4 << 2) + tid; e2 < total; e2 += NT) {
             const int r2 = e2 / rowf;
-            g[e2] = s[r2 * srow + col0 + (e2 - r2 * rowf)];
+            const float v = s[r2 * srow + col0 + (e2 - r2 * rowf)];
+            g[e2] = accumulate ? g[e2] + v : v;
         }
     } else {
         for (int e2 = tid; e2 < total; e2 += NT) {
             const int r2 = e2 / rowf;
-            g[e2] = s[r2 * srow + col0 + (e2 - r2 * rowf)];
+            const float v = s[r2 * srow + col0 + (e2 - r2 * rowf)];
+            g[e2] = accumulate ? g[e2] + v : v;
         }
     }
 }

@@ -59,6 +59,7 @@ struct PreprocessBwdParams {
     int grad_stride;  // floats per record
     int n_channels_pad;  // round_up4(blended channels) = offset of the geometry terms inside a record
     int F, Fi, include_feature, render_geo;
+    int accumulate;  // parameter gradients: out += value (multi-view accumulation) instead of out = value
     // per-tensor outputs in the reference's layouts (every row written; zeros for culled splats)
     float* dL_dmean2D;      // (P,3)
     float* dL_dmean2D_abs;  // (P,3)

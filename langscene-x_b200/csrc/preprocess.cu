@@ -313,17 +313,21 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
     p.dL_dmean2D_abs[3 * idx + 1] = ggeo[3];
     p.dL_dmean2D_abs[3 * idx + 2] = 0.f;
     reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(ggeo[4], ggeo[5], 0.f, ggeo[6]);
-    p.dL_dopacity[idx] = ggeo[7];
+    const bool acc = p.accumulate != 0;
+    auto put = [acc](float* dst, const float v) { *dst = acc ? *dst + v : v; };
+    put(p.dL_dopacity + idx, ggeo[7]);
 
     if (!(p.radii[idx] > 0)) {
         // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
+        if (!acc) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
+            for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = 0.f;
+            for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
-        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
+            reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (g_sh)
             for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
         return;
@@ -374,7 +378,7 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < 6; ++i) g_cov[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = g_cov[i];
+    for (int i = 0; i < 6; ++i) put(p.dL_dcov3D + 6 * idx + i, g_cov[i]);
 
     // gradient w.r.t. the upper 2x3 block of T
     float tv0[3], tv1[3];  // (row of T) . V columns
@@ -515,9 +519,9 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
     }
 
-    p.dL_dmeans3D[3 * idx + 0] = g_mean.x;
-    p.dL_dmeans3D[3 * idx + 1] = g_mean.y;
-    p.dL_dmeans3D[3 * idx + 2] = g_mean.z;
+    put(p.dL_dmeans3D + 3 * idx + 0, g_mean.x);
+    put(p.dL_dmeans3D + 3 * idx + 1, g_mean.y);
+    put(p.dL_dmeans3D + 3 * idx + 2, g_mean.z);
 
     // ---- part 4: world covariance -> scale / rotation (backward.cu:278-341) ------------------------
     if (p.scales != nullptr) {
@@ -559,9 +563,9 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         const Mat3 Rt = mat3_transpose(R);
         Mat3 gMt = mat3_transpose(gM);
 
-        p.dL_dscales[3 * idx + 0] = Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2];
-        p.dL_dscales[3 * idx + 1] = Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2];
-        p.dL_dscales[3 * idx + 2] = Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2];
+        put(p.dL_dscales + 3 * idx + 0, Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2]);
+        put(p.dL_dscales + 3 * idx + 1, Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2]);
+        put(p.dL_dscales + 3 * idx + 2, Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2]);
 
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
@@ -577,8 +581,12 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
                4 * y * (gMt.m[2][2] + gMt.m[0][0]);
         gq.w = 2 * r * (gMt.m[0][1] - gMt.m[1][0]) + 2 * x * (gMt.m[2][0] + gMt.m[0][2]) + 2 * y * (gMt.m[1][2] + gMt.m[2][1]) -
                4 * z * (gMt.m[1][1] + gMt.m[0][0]);
+        if (acc) {
+            const float4 o = reinterpret_cast<const float4*>(p.dL_drotations)[idx];
+            gq = make_float4(gq.x + o.x, gq.y + o.y, gq.z + o.z, gq.w + o.w);
+        }
         reinterpret_cast<float4*>(p.dL_drotations)[idx] = gq;  // w.r.t. the raw (un-normalised) quaternion
-    } else {
+    } else if (!acc) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
         reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -602,18 +610,19 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
     if ((int)threadIdx.x < rows)
         preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, s_rec + threadIdx.x * rec_row);
     __syncthreads();
-    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row);
-    slab_store<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, s_rec, rows, 3, rec_row, 0);
+    const bool acc = p.accumulate != 0;
+    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, acc);
+    slab_store<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, s_rec, rows, 3, rec_row, 0, acc);
     int c = 3;
     if (p.include_feature) {
-        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, s_rec, rows, p.F, rec_row, c);
+        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, s_rec, rows, p.F, rec_row, c, acc);
         c += p.F;
-        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, s_rec, rows, p.Fi, rec_row, c);
+        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, s_rec, rows, p.Fi, rec_row, c, acc);
         c += p.Fi;
     }
     if (p.render_geo) {
-        slab_store<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, s_rec, rows, 5, rec_row, c);
-    } else {
+        slab_store<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, s_rec, rows, 5, rec_row, c, acc);
+    } else if (!acc) {
         for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
     }
 }

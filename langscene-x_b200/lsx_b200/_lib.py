@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("LSX_B200_LIB", os.path.join(_PKG_DIR, "liblsx_b200.so
 
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_BLEND_CHANNELS = 40
 
 
@@ -54,6 +54,7 @@ class BackwardArgs(ctypes.Structure):
         ("dL_dmeans3D", c_void_p), ("dL_dcov3D", c_void_p), ("dL_dsh", c_void_p), ("dL_dscales", c_void_p),
         ("dL_drotations", c_void_p), ("dL_dall_map", c_void_p),
         ("stream", c_void_p),
+        ("accumulate_param_grads", c_int32),
     ]
 
 

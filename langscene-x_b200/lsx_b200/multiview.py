@@ -63,6 +63,11 @@ class GradArena:
             v.add_(g.reshape(v.shape))
         return self
 
+    def grad_buffers(self) -> Dict[str, torch.Tensor]:
+        """The arena's groups keyed like `ops.rasterize_gaussians_backward(..., grad_buffers=, accumulate=True)` expects:
+        the backward kernel then adds each view's parameter gradients straight into the arena."""
+        return {name: v for name, v in self.views.items() if v.numel() > 0}
+
     def all_reduce(self, group=None, async_op=False):
         """Sum over ranks with ONE collective on the flat buffer."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -165,7 +165,13 @@ def rasterize_gaussians_backward(
     scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
     dL_dout_color, dL_dout_language_feature, dL_dout_language_feature_instance, dL_dout_all_map, dL_dout_plane_depth,
     sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, render_geo, debug, include_feature,
+    *, grad_buffers=None, accumulate=False,
 ):
+    """Positional signature of the reference's `_C.rasterize_gaussians_backward`.  Keyword-only extensions for
+    multi-view optimisation: `grad_buffers` maps any of {"means3D", "sh", "opacity", "scales", "rotations", "colors",
+    "language_feature", "instance_feature", "all_map", "cov3D"} to a caller-owned contiguous fp32 tensor (e.g. a view
+    into lsx_b200.multiview.GradArena) that receives that gradient instead of a fresh tensor; with `accumulate=True`
+    the parameter gradients are ADDED to those buffers (the kernel does the read-modify-write, no extra pass)."""
     lib = _lib.load()
     if not means3D.is_cuda:
         raise RuntimeError("means3D must be a CUDA tensor (this operator has no CPU path)")
@@ -211,6 +217,27 @@ def rasterize_gaussians_backward(
         if not include_feature:
             g_lang.zero_()
             g_inst.zero_()
+        if grad_buffers:
+            own = {"means3D": g_means3D, "sh": g_sh, "opacity": g_opacity, "scales": g_scales, "rotations": g_rot,
+                   "colors": g_colors, "language_feature": g_lang, "instance_feature": g_inst, "all_map": g_all_map,
+                   "cov3D": g_cov3D}
+            for name, buf in grad_buffers.items():
+                ref = own[name]
+                if buf.numel() != ref.numel() or buf.dtype != _FLOAT or not buf.is_contiguous() or buf.device != device:
+                    raise RuntimeError(f"grad_buffers[{name!r}] must be a contiguous float32 tensor of {ref.numel()} elements on {device}")
+                own[name] = buf.view(ref.shape)
+            (g_means3D, g_sh, g_opacity, g_scales, g_rot, g_colors, g_lang, g_inst, g_all_map, g_cov3D) = (
+                own[k] for k in ("means3D", "sh", "opacity", "scales", "rotations", "colors", "language_feature",
+                                 "instance_feature", "all_map", "cov3D"))
+        if accumulate:
+            if not grad_buffers:
+                raise RuntimeError("accumulate=True needs caller-owned grad_buffers to accumulate into")
+            for name, t in (("means3D", g_means3D), ("sh", g_sh), ("opacity", g_opacity), ("scales", g_scales),
+                            ("rotations", g_rot), ("colors", g_colors), ("language_feature", g_lang),
+                            ("instance_feature", g_inst), ("all_map", g_all_map), ("cov3D", g_cov3D)):
+                if name not in grad_buffers:
+                    t.zero_()  # library-owned outputs start from zero so that "+=" equals "="
+
         if P != 0:
             a = _lib.BackwardArgs()
             a.P, a.D, a.M, a.W, a.H, a.F, a.Fi, a.R = P, int(degree), M, W, H, F, Fi, int(R)
@@ -234,6 +261,7 @@ def rasterize_gaussians_backward(
             a.dL_dsh = g_sh.data_ptr() if M > 0 else None
             a.dL_dscales, a.dL_drotations, a.dL_dall_map = g_scales.data_ptr(), g_rot.data_ptr(), g_all_map.data_ptr()
             a.stream = _stream_handle(device)
+            a.accumulate_param_grads = int(bool(accumulate))
             _lib.check(lib.lsx_rasterize_backward(ctypes.byref(a)), "rasterize_gaussians_backward")
 
     return (g_means2D, g_means2D_abs, g_colors, g_lang, g_inst, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot,

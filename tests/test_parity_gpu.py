@@ -344,6 +344,34 @@ def test_footprint_culling_is_conservative(s_med, aniso, opac_shift, seed):
                  check_grads=opac_shift >= 0)
 
 
+def test_backward_accumulates_into_caller_buffers():
+    """Multi-view path: backward(..., grad_buffers=arena views, accumulate=True) over two views must equal the sum of
+    the two views' ordinary backward results (parity target = single-GPU gradient accumulation)."""
+    from lsx_b200.multiview import GradArena, BWD_TO_GROUP
+    from lsx_b200.synthetic import make_camera
+    ops = _new()
+    P, W, H, F = 20_000, 256, 192, 16
+    scene, cam0, grads = _scene(P, W, H, F, seed=31)
+    cams = [cam0, make_camera(W, H, yaw_deg=9.0).to("cuda:0")]
+    bg = torch.tensor([0.3, 0.2, 0.1], device="cuda:0")
+    arena = GradArena.allocate(P, 16, F, 3, "cuda:0")
+    expect = {}
+    for cam in cams:
+        fargs = hz.native_forward_args(scene, cam, bg, F)
+        fwd, bwd = hz.run_native(ops, fargs, grads)
+        for k, gname in BWD_TO_GROUP.items():
+            expect[gname] = bwd[k].clone() if gname not in expect else expect[gname] + bwd[k]
+        fwd2 = dict(zip(hz.FWD_NAMES, ops.rasterize_gaussians(*fargs)))
+        out = ops.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd2, grads),
+                                               grad_buffers=arena.grad_buffers(), accumulate=True)
+        bw2 = dict(zip(hz.BWD_NAMES, out))
+        assert bw2["sh"].data_ptr() == arena.views["sh"].data_ptr()          # written in place, no copy
+        assert hz.rel_err(bw2["means2D"], bwd["means2D"]) < 1e-5              # per-view outputs are not accumulated
+    for gname, v in arena.views.items():
+        if v.numel():
+            assert hz.rel_err(v, expect[gname].reshape(v.shape)) < 2e-5, gname
+
+
 def test_no_memory_growth_without_cyclic_gc():
     """Scratch, outputs and gradients must be released by reference counting alone (a ctypes callback capturing its
     owner once kept every call's ~400 B/Gaussian scratch alive until the cyclic collector ran)."""
