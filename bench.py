@@ -37,6 +37,8 @@ import torch.distributed as dist  # noqa: E402
 METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
 NCU_TRAFFIC = {"render_bwd": 608793344, "render_fwd": 370414848}
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: what actually bounds these kernels
+NCU_ISSUE_BUSY_PCT = {"render_bwd": 69.5, "render_fwd": 90.4}
 
 
 def load_peaks():
@@ -507,7 +509,7 @@ def main():
         ach = kbytes / (stages[dom] * 1e-3) / 1e9
         out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                            "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
-                           "launch_ms": stages[dom],
+                           "launch_ms": stages[dom], "issue_slots_busy_pct_ncu": NCU_ISSUE_BUSY_PCT,
                            "note": "the render kernels are FP32 instruction-issue bound, not HBM bound (DESIGN.md 3, profiles/): "
                                    "algorithmic bytes per launch = R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd), "
                                    "means over this rank's views; `traffic` = dram bytes of one ncu --set full capture of view 0"}
