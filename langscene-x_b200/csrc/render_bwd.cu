@@ -57,40 +57,14 @@ struct WarpTransposeReduce {
     }
 };
 
-template <int CT4, int CHUNK>
-__global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
-    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    constexpr int GS = CT4 + 8;                // floats per packed gradient record
-    constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
-    constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
-    using Stage = WarpStage<RS, CHUNK>;
-    static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
-
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(16) float s_w[2][32];  // weight exchange, double buffered
-
-    const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
-    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
-    const unsigned lane = threadIdx.x;
-    const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
-    const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < p.W && py < p.H;
-    const float pxf = (float)px, pyf = (float)py;
-    const size_t HW = (size_t)p.H * p.W;
-    const size_t pix = (size_t)py * p.W + px;
-
-    const uint2 range = p.ranges[tile];
-    const int n = (int)(range.y - range.x);
-
-    // ---- per-pixel state -------------------------------------------------------------------------
-    const float T_final = inside ? p.final_T[pix] : 0.f;
-    float T = T_final;
-    const int last_contributor = inside ? (int)p.n_contrib[pix] : 0;
-
-    float g[CT4];  // upstream gradient of every blended channel of this pixel
+// Upstream gradient of every blended channel at one pixel (planar inputs), with the plane-depth gradient folded
+// into the map channels (backward.cu:479-503); bg_dot = <background, dL/dcolor>.
+template <int CT4>
+__device__ __forceinline__ void load_pixel_gradients(const RenderParams& p, const bool inside, const size_t pix, const size_t HW,
+                                                     const float pxf, const float pyf, float (&g)[CT4], float& bg_dot) {
 #pragma unroll
     for (int c = 0; c < CT4; ++c) g[c] = 0.f;
-    float bg_dot = 0.f;
+    bg_dot = 0.f;
     if (inside) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -132,6 +106,42 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             }
         }
     }
+
+}
+
+template <int CT4, int CHUNK>
+__global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
+    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    constexpr int GS = CT4 + 8;                // floats per packed gradient record
+    constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
+    constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
+    using Stage = WarpStage<RS, CHUNK>;
+    static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(16) float s_w[2][32];  // weight exchange, double buffered
+
+    const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
+    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
+    const unsigned lane = threadIdx.x;
+    const int px = tile_x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const int py = tile_y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < p.W && py < p.H;
+    const float pxf = (float)px, pyf = (float)py;
+    const size_t HW = (size_t)p.H * p.W;
+    const size_t pix = (size_t)py * p.W + px;
+
+    const uint2 range = p.ranges[tile];
+    const int n = (int)(range.y - range.x);
+
+    // ---- per-pixel state -------------------------------------------------------------------------
+    const float T_final = inside ? p.final_T[pix] : 0.f;
+    float T = T_final;
+    const int last_contributor = inside ? (int)p.n_contrib[pix] : 0;
+
+    float g[CT4];  // upstream gradient of every blended channel of this pixel
+    float bg_dot = 0.f;
+    load_pixel_gradients<CT4>(p, inside, pix, HW, pxf, pyf, g, bg_dot);
 
     // deepest contributor of the block: list entries at or beyond it are never blended by any of its pixels
     const int n_eff = min(__reduce_max_sync(kFull, last_contributor), n);
