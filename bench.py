@@ -192,13 +192,15 @@ def batch_stepper(mod, views, grads, arena, world):
     fused = hasattr(mod, "distCUDA2")  # lsx_b200.ops: its backward accumulates straight into the arena
 
     def step():
-        arena.zero_()
-        for vw in views:
+        if not fused:
+            arena.zero_()
+        for i, vw in enumerate(views):
             fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*vw["fargs"])))
             bargs = hz.native_backward_args(vw["fargs"], fwd, grads)
             if fused:
+                # the first view of a step overwrites the arena (every row is written), the others add to it
                 bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*bargs, grad_buffers=arena.grad_buffers(),
-                                                                              accumulate=True)))
+                                                                              accumulate=i > 0)))
             else:
                 bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*bargs)))
                 arena.accumulate({g: bwd[k] for k, g in BWD_TO_GROUP.items()})

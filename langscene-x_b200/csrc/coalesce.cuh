@@ -72,6 +72,8 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
         int e = tid * 4;
         int r = e / rowf, c = e - r * rowf;
         for (int i = tid; i < n4; i += NT) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) o = reinterpret_cast<const float4*>(g)[i];  // issued first: overlaps the shared-memory reads
             float vv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -83,7 +85,6 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
                 vv[k] = s[rk * srow + col0 + ck];
             }
             if (accumulate) {
-                const float4 o = reinterpret_cast<const float4*>(g)[i];
                 vv[0] += o.x;
                 vv[1] += o.y;
                 vv[2] += o.z;

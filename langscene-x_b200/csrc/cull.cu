@@ -12,10 +12,10 @@
 // have executed `continue` in the reference, so every output (including n_contrib / final_T / out_observe)
 // is unchanged.
 //
-// The test is exact up to a safety margin: the maximum of `power` over the block's continuous rectangle
-// (a convex quadratic minimised over a box: centre inside -> 0, otherwise the minimum over the four edges)
-// is compared with ln(1 / (255 opacity)); the margin (1e-3 + 1e-4 * magnitude of the terms) is >= 100x the
-// fp32 rounding error of either evaluation, and every comparison is written so that NaN / non-convex /
+// The test is exact up to a safety margin: the maximum of `power` over the block's continuous cell (widened by
+// half a pixel; a convex quadratic minimised over a box: centre inside -> 0, otherwise the minimum over the four
+// edges) is compared with ln(1 / (255 opacity)); the margin (1e-3 + 1e-4 * magnitude of the terms) is >= 100x
+// the fp32 rounding error of either evaluation, and every comparison is written so that NaN / non-convex /
 // non-finite inputs keep the bit SET (the render kernel then applies the reference's own tests).
 #include "kernels.cuh"
 
@@ -23,31 +23,64 @@ namespace lsx {
 
 namespace {
 
-struct SplatHead {
-    float mx, my, a, b, c, o;
-};
-
-// true if the splat can pass the alpha test somewhere in pixels [x0, x0+nx) x [y0, y0+ny)
-__device__ __forceinline__ bool block_may_blend(const SplatHead& s, const float thr, const float inv_a, const float inv_c,
-                                                const float x0, const float y0, const float nx,
-                                                const float ny) {
-    // offsets d = mean - pixel over the block: dx in [dxl, dxh], dy in [dyl, dyh]
-    const float dxh = s.mx - x0, dxl = s.mx - (x0 + nx - 1.0f);
-    const float dyh = s.my - y0, dyl = s.my - (y0 + ny - 1.0f);
-    if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return true;  // centre inside the block
-    const float b2 = 2.0f * s.b;
-    auto q = [&](float dx, float dy) { return s.a * dx * dx + b2 * dx * dy + s.c * dy * dy; };
-    // edges dx = const: minimise over dy;  edges dy = const: minimise over dx
-    const float dy1 = fminf(dyh, fmaxf(dyl, -s.b * dxl * inv_c));
-    const float dy2 = fminf(dyh, fmaxf(dyl, -s.b * dxh * inv_c));
-    const float dx3 = fminf(dxh, fmaxf(dxl, -s.b * dyl * inv_a));
-    const float dx4 = fminf(dxh, fmaxf(dxl, -s.b * dyh * inv_a));
-    const float qmin = fminf(fminf(q(dxl, dy1), q(dxh, dy2)), fminf(q(dx3, dyl), q(dx4, dyh)));
-    const float DX = fmaxf(fabsf(dxl), fabsf(dxh)), DY = fmaxf(fabsf(dyl), fabsf(dyh));
-    const float qscale = s.a * DX * DX + fabsf(b2) * DX * DY + s.c * DY * DY;
-    // max power = -0.5 qmin ; blend needs power >= thr
-    const bool never = (-0.5f * qmin) < (thr - (1.0e-3f + 1.0e-4f * (qscale + fabsf(thr))));
-    return !never;
+// One list entry: footprint mask over the 2 x 4 grid of 8x4-pixel blocks of its tile.
+//
+// The blocks are widened by half a pixel to the continuous cells [x0 - .5 + 8 i, +8] x [y0 - .5 + 4 j, +4], so that
+// neighbouring blocks share their edges: 3 vertical lines x 4 intervals + 5 horizontal lines x 2 intervals = 22
+// one-dimensional minimisations of  q(dx, dy) = a dx^2 + 2 b dx dy + c dy^2  (4 instructions each once the line's
+// coefficients are set up) give the exact minimum of q over every cell whose interior does not contain the centre.
+__device__ __forceinline__ unsigned footprint_mask(const float mx, const float my, const float a, const float b, const float c,
+                                                   const float o, const float tx0, const float ty0) {
+    const float o255 = o * 255.0f;
+    // every comparison is written so that NaN / non-finite / non-convex inputs fall through to "visit everywhere"
+    const bool convex = (a > 0.f) && (c > 0.f) && (a * c - b * b > 0.f) && (a < 1.0e6f) && (c < 1.0e6f) &&
+                        (fabsf(mx) < 1.0e7f) && (fabsf(my) < 1.0e7f);  // => every term below is finite
+    if (!convex || !(o255 < 3.0e38f)) return 0xffu;
+    if (o255 < 0.999f) return 0u;  // power <= 0 for a convex form, so alpha <= opacity < 1/255 everywhere
+    const float thr = -logf(o255);   // blend needs  -0.5 q >= thr
+    const float inv_a = 1.0f / a, inv_c = 1.0f / c;
+    // d = mean - pixel; cell boundaries in d-space (descending in i because d = mean - coordinate)
+    float dxl[3], dyl[5];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) dxl[i] = mx - (tx0 - 0.5f + 8.0f * (float)i);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) dyl[j] = my - (ty0 - 0.5f + 4.0f * (float)j);
+    // safety margin: >= 100x the fp32 rounding error of either evaluation of the form anywhere in the tile
+    const float DX = fmaxf(fabsf(dxl[0]), fabsf(dxl[2])), DY = fmaxf(fabsf(dyl[0]), fabsf(dyl[4]));
+    const float qscale = a * DX * DX + 2.0f * fabsf(b) * DX * DY + c * DY * DY;
+    const float qmax = -2.0f * (thr - (1.0e-3f + 1.0e-4f * (qscale + fabsf(thr))));  // keep iff q_min <= qmax
+    // vertical lines dx = dxl[i]: q = A + dy (B + c dy), minimised at dy = t
+    float qv[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float A = a * dxl[i] * dxl[i], B = 2.0f * b * dxl[i], t = -b * dxl[i] * inv_c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float dy = fminf(dyl[j], fmaxf(dyl[j + 1], t));  // interval [dyl[j+1], dyl[j]]
+            qv[i][j] = A + dy * (B + c * dy);
+        }
+    }
+    // horizontal lines dy = dyl[j]
+    float qh[5][2];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const float A = c * dyl[j] * dyl[j], B = 2.0f * b * dyl[j], t = -b * dyl[j] * inv_a;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float dx = fminf(dxl[i], fmaxf(dxl[i + 1], t));  // interval [dxl[i+1], dxl[i]]
+            qh[j][i] = A + dx * (B + a * dx);
+        }
+    }
+    unsigned m = 0u;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const int i = w & 1, j = w >> 1;
+        const bool centre_inside = (dxl[i + 1] <= 0.f) && (dxl[i] >= 0.f) && (dyl[j + 1] <= 0.f) && (dyl[j] >= 0.f);
+        const float qmin = fminf(fminf(qv[i][j], qv[i + 1][j]), fminf(qh[j][i], qh[j + 1][i]));
+        const bool never = !centre_inside && (qmin > qmax);
+        m |= never ? 0u : (1u << w);
+    }
+    return m;
 }
 
 __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __restrict__ ranges,
@@ -61,25 +94,7 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
         const float* rec = records + (size_t)point_list[i] * rec_stride;
         const float4 h0 = __ldg(reinterpret_cast<const float4*>(rec));
         const float2 h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
-        SplatHead s{h0.x, h0.y, h0.z, h0.w, h1.x, h1.y};
-        unsigned m = 0xffu;  // default (NaN / non-finite / non-convex inputs): visit everywhere
-        const float o255 = s.o * 255.0f;
-        const bool convex = (s.a > 0.f) && (s.c > 0.f) && (s.a * s.c - s.b * s.b > 0.f) && (s.a < 1.0e6f) &&
-                            (s.c < 1.0e6f) && (fabsf(s.mx) < 1.0e7f) && (fabsf(s.my) < 1.0e7f);  // => every term finite
-        if (convex && o255 < 0.999f) {
-            m = 0u;  // power <= 0 for a convex form, so alpha <= opacity < 1/255 everywhere
-        } else if (convex && o255 < 3.0e38f) {
-            const float thr = -logf(o255);
-            const float inv_a = 1.0f / s.a, inv_c = 1.0f / s.c;
-            m = 0u;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                const bool keep = block_may_blend(s, thr, inv_a, inv_c, tx0 + (float)((w & 1) * 8),
-                                                  ty0 + (float)((w >> 1) * 4), 8.0f, 4.0f);
-                m |= keep ? (1u << w) : 0u;
-            }
-        }
-        masks[i] = (uint8_t)m;
+        masks[i] = (uint8_t)footprint_mask(h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, tx0, ty0);
     }
 }
 
