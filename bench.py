@@ -338,11 +338,11 @@ def algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi):
 
 
 def run_cpu_sample(threads=None):
-    """The CPU restatement on a bounded sample: the C3 generator scaled by 1/16 in pixels and Gaussians
-    (480x270, 62 500 Gaussians, same splat size in pixels => same per-pixel list statistics), fwd+bwd once."""
+    """The CPU restatement on a bounded sample: the C3 generator scaled by 1/4 in pixels and Gaussians
+    (960x540, 250 000 Gaussians, same splat size in pixels => same per-pixel list statistics), fwd+bwd, best of 2."""
     from oracle import oracle as orc
     from lsx_b200.synthetic import make_all_map, make_camera, make_scene, make_upstream_grads
-    P, W, H, F = 62_500, 480, 270, 16
+    P, W, H, F = 250_000, 960, 540, 16
     if threads:
         orc.set_num_threads(threads)
     scene, cam = make_scene(P, W, H, F=F, seed=0), make_camera(W, H)
@@ -359,7 +359,7 @@ def run_cpu_sample(threads=None):
                                n(g["plane_depth"]))
         best = min(best, time.perf_counter() - t0)
     return {"value": W * H / best / 1e6, "unit": "MPix/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"oracle/lsx_oracle.c (OpenMP) fwd+bwd, best of 2, on the C3 generator scaled 1/16: {P} Gaussians, "
+            "sample": f"oracle/lsx_oracle.c (OpenMP) fwd+bwd, best of 2, on the C3 generator scaled 1/4: {P} Gaussians, "
                       f"{W}x{H}, F=16 (+3 instance, +5 map), R={o['num_rendered']}, {best:.2f} s/iter; "
                       f"host has {os.cpu_count()} logical cores"}
 
