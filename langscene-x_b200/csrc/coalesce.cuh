@@ -17,33 +17,39 @@ namespace lsx {
 __host__ __device__ static inline int padded_row(int row_floats) { return row_floats | 1; }
 
 // global (rows x rowf, contiguous) -> smem (row stride srow).  `g` points at the slab's first element.
+// Four independent 16-B loads are issued per thread before any of them is consumed: these kernels are bound by
+// memory latency (few resident warps because of the tile), so bytes in flight per thread is what matters.
 template <int NT>
 __device__ __forceinline__ void slab_load(float* __restrict__ s, const float* __restrict__ g, int rows, int rowf, int srow) {
     const int total = rows * rowf;
     const int tid = threadIdx.x;
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0 && rowf >= 4) {
         const int n4 = total >> 2;
-        const int step = NT * 4;
-        const int dq = step / rowf, dr = step - dq * rowf;
-        int e = tid * 4;
-        int r = e / rowf, c = e - r * rowf;
-        for (int i = tid; i < n4; i += NT) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
+        constexpr int U = 4;
+        for (int i0 = tid; i0 < n4; i0 += NT * U) {
+            float4 v[U];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                int ck = c + k, rk = r;
-                if (ck >= rowf) {
-                    ck -= rowf;
-                    ++rk;
-                }
-                s[rk * srow + ck] = vv[k];
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * NT;
+                v[u] = (i < n4) ? __ldg(reinterpret_cast<const float4*>(g) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            r += dq;
-            c += dr;
-            if (c >= rowf) {
-                c -= rowf;
-                ++r;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * NT;
+                if (i < n4) {
+                    const int e = i * 4;
+                    const int r = e / rowf, c = e - r * rowf;
+                    const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int ck = c + k, rk = r;
+                        if (ck >= rowf) {
+                            ck -= rowf;
+                            ++rk;
+                        }
+                        s[rk * srow + ck] = vv[k];
+                    }
+                }
             }
         }
         for (int e2 = (n4 << 2) + tid; e2 < total; e2 += NT) {
