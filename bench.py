@@ -542,7 +542,7 @@ def main():
             rsteps = max(2, args.steps // 4)
             rms = time_loop(rstep, rsteps, 1, 1) / rsteps
             out["ref_cuda"] = {"ms_per_step": rms, "ms_per_iter": rms / V, "value": V * W * H / (rms * 1e-3) / 1e6, "unit": "MPix/s",
-                               "what": "reference CUDA rasterizer (oracle/_ref/ref_rast_f16.so, sm_100a recompile), same step, same process",
+                               "what": f"reference CUDA rasterizer (oracle/_ref/ref_rast_f{16 if F == 16 else 3}.so, sm_100a recompile), same step, same process",
                                "speedup_device_resident": rms / ms_step}
         if not args.no_cpu_baseline:
             try:

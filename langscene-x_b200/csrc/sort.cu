@@ -113,8 +113,13 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __
 // ---------------------------------------------------------------------------------------------
 // radix sort pass
 // ---------------------------------------------------------------------------------------------
+// ghist == nullptr: digit-major per-block histogram hist[d * nb + b] (scanned by exclusive_scan_u32 afterwards).
+// ghist != nullptr: "short sort" mode for arrays of at most kShortSortBlocks blocks — block-major hist[b * 256 + d]
+// plus global digit totals in ghist[256]; the scatter kernel derives its offsets from these itself, so a pass is
+// two launches instead of five (sorts of <= 2 M keys are bound by launch latency, not bandwidth).
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
-                                                              uint32_t mask, uint32_t* __restrict__ hist, int nb) {
+                                                              uint32_t mask, uint32_t* __restrict__ hist, int nb,
+                                                              uint32_t* __restrict__ ghist) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -125,7 +130,12 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
         if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
     }
     __syncthreads();
-    if (threadIdx.x <= mask) hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    if (ghist == nullptr) {
+        if (threadIdx.x <= mask) hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    } else {
+        hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
+        if (h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], h[threadIdx.x]);
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
@@ -133,8 +143,17 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
                                                                  uint32_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int n, int shift,
                                                                  uint32_t mask, const uint32_t* __restrict__ offsets,
-                                                                 int nb) {
+                                                                 int nb, const uint32_t* __restrict__ ghist) {
     __shared__ uint32_t cnt[kWarps][256];
+    __shared__ uint32_t s_warp[32];
+    uint32_t short_start = 0;  // short-sort mode: global position of this block's first key with digit threadIdx.x
+    if (ghist != nullptr) {
+        uint32_t total;
+        const uint32_t digit_base = block_exclusive_scan(ghist[threadIdx.x], s_warp, total);
+        uint32_t before = 0;  // keys with this digit in earlier blocks (block-major histogram: coalesced over digits)
+        for (int b = 0; b < (int)blockIdx.x; ++b) before += offsets[b * 256 + threadIdx.x];
+        short_start = digit_base + before;
+    }
     for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&cnt[0][0])[i] = 0;
     __syncthreads();
 
@@ -169,7 +188,7 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     {
         const uint32_t d = threadIdx.x;
         if (d <= mask) {
-            uint32_t run = offsets[d * nb + blockIdx.x];
+            uint32_t run = ghist != nullptr ? short_start : offsets[d * nb + blockIdx.x];
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
                 const uint32_t t = cnt[w][d];
@@ -212,9 +231,12 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out
     return 0;
 }
 
+constexpr int kShortSortBlocks = 512;  // <= 2 M keys
+constexpr int kMaxPasses = 4;          // 32-bit keys, 8-bit digits
+
 size_t radix_sort_temp_bytes(int n) {
     const int nb = ceil_div(n > 0 ? n : 1, kTile);
-    return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + scan_temp_bytes(256 * nb);
+    return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + scan_temp_bytes(256 * nb) + kMaxPasses * 256 * sizeof(uint32_t);
 }
 
 int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_bit, int end_bit, bool identity_vals,
@@ -223,19 +245,27 @@ int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_
     if (n <= 0) return 0;
     const int nb = ceil_div(n, kTile);
     uint32_t* hist = static_cast<uint32_t*>(temp);
-    void* scan_temp = static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256);
+    char* after_hist = static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256);
+    void* scan_temp = after_hist;
+    uint32_t* ghist_all = reinterpret_cast<uint32_t*>(after_hist + scan_temp_bytes(256 * nb));
+    const bool short_mode = nb <= kShortSortBlocks && radix_sort_num_passes(begin_bit, end_bit) <= kMaxPasses;
+    if (short_mode) LSX_CUDA_OK(cudaMemsetAsync(ghist_all, 0, kMaxPasses * 256 * sizeof(uint32_t), stream));
     int cur = 0;
     bool first = true;
-    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+    int pass = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8, ++pass) {
         const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
         const uint32_t mask = (1u << bits) - 1u;
-        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, nb);
+        uint32_t* ghist = short_mode ? ghist_all + pass * 256 : nullptr;
+        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, nb, ghist);
         LSX_KERNEL_OK(stream, debug);
-        int rc = exclusive_scan_u32(hist, nullptr, hist, (int)(mask + 1) * nb, nullptr, scan_temp, stream, debug);
-        if (rc) return rc;
+        if (!short_mode) {
+            int rc = exclusive_scan_u32(hist, nullptr, hist, (int)(mask + 1) * nb, nullptr, scan_temp, stream, debug);
+            if (rc) return rc;
+        }
         const uint32_t* vin = (first && identity_vals) ? nullptr : vals[cur];
         radix_scatter_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
-                                                          hist, nb);
+                                                          hist, nb, ghist);
         LSX_KERNEL_OK(stream, debug);
         cur ^= 1;
         first = false;
