@@ -15,7 +15,8 @@
 // Pass structure (8-bit digits): per-block digit histogram -> exclusive scan (digit-major) -> stable
 // scatter.  In the scatter kernel each warp owns a contiguous 512-key segment and ranks its keys with
 // __match_any_sync against warp-private shared-memory counters; a 256-thread step turns the per-warp
-// counters into global positions.  No inter-block spinning anywhere (see B200_PROFILING.md on why).
+// counters into block-local and global positions; the block's 4096 pairs are regrouped by digit in shared
+// memory and leave as contiguous runs (coalesced stores instead of 4-byte scatters).  No inter-block spinning anywhere (see B200_PROFILING.md on why).
 #include "kernels.cuh"
 
 namespace lsx {
@@ -146,6 +147,8 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
                                                                  int nb, const uint32_t* __restrict__ ghist) {
     __shared__ uint32_t cnt[kWarps][256];
     __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_key[kTile], s_val[kTile];   // the block's pairs regrouped by digit before they leave
+    __shared__ uint32_t s_lstart[256], s_gbase[256];  // per digit: start inside the block / in the output array
     uint32_t short_start = 0;  // short-sort mode: global position of this block's first key with digit threadIdx.x
     if (ghist != nullptr) {
         uint32_t total;
@@ -185,28 +188,45 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
         __syncwarp();
     }
     __syncthreads();
+    // per digit: block total -> block-local start (exclusive scan over digits), per-warp local starts, global start
     {
         const uint32_t d = threadIdx.x;
-        if (d <= mask) {
-            uint32_t run = ghist != nullptr ? short_start : offsets[d * nb + blockIdx.x];
+        uint32_t total_d = 0;
 #pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const uint32_t t = cnt[w][d];
-                cnt[w][d] = run;
-                run += t;
-            }
+        for (int w = 0; w < kWarps; ++w) total_d += cnt[w][d];
+        uint32_t block_total;
+        const uint32_t lstart = block_exclusive_scan(total_d, s_warp, block_total);
+        uint32_t run = lstart;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = cnt[w][d];
+            cnt[w][d] = run;
+            run += t;
         }
+        s_lstart[d] = lstart;
+        s_gbase[d] = d <= mask ? (ghist != nullptr ? short_start : offsets[d * nb + blockIdx.x]) : 0u;
     }
     __syncthreads();
+    // local shuffle: the block's keys (and values) land in shared memory grouped by digit, in stable order
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int idx = wbase + i * 32 + lane;
         if (idx < n) {
             const uint32_t d = (key[i] >> shift) & mask;
-            const uint32_t pos = cnt[warp][d] + rank[i];
-            keys_out[pos] = key[i];
-            vals_out[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            const uint32_t lp = cnt[warp][d] + rank[i];
+            s_key[lp] = key[i];
+            s_val[lp] = vals_in ? vals_in[idx] : (uint32_t)idx;
         }
+    }
+    __syncthreads();
+    // write out: consecutive threads write consecutive positions of a digit's run (coalesced within runs)
+    const int count = min(kTile, n - (int)blockIdx.x * kTile);
+    for (int j = threadIdx.x; j < count; j += kThreads) {
+        const uint32_t k = s_key[j];
+        const uint32_t d = (k >> shift) & mask;
+        const uint32_t pos = s_gbase[d] + ((uint32_t)j - s_lstart[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = s_val[j];
     }
 }
 
