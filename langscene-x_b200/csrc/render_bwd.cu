@@ -115,11 +115,19 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
     constexpr int GS = CT4 + 8;                // floats per packed gradient record
     constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
     constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
+    // Lanes CT4..31 have no channel to sum in the outer-product phase: they sum geometry terms instead (the term's
+    // 32 per-pixel values are exchanged like the weights, the lane's "gradient view" is all ones).  NGL terms go
+    // that way, the remaining NB = 8 - NGL through the shuffle butterfly.  Only the all-or-nothing split is used:
+    // with 27 channels (4 free lanes) the mixed variant costs 27 more registers than it saves in instructions
+    // (measured: 2.56 -> 2.66 ms at C3), with <= 24 channels all 8 terms fit (C4: 0.51 -> 0.44 ms).
+    constexpr int NGL = (NPASS == 1 && 32 - CT4 >= 8) ? 8 : 0;
+    constexpr int NB = (8 - NGL) == 0 ? 0 : ((8 - NGL) <= 4 ? 4 : 8);   // butterfly width (power of two)
+    constexpr int XROW = 36;                   // floats between exchanged arrays: 16-B aligned, bank offset 4 per array
     using Stage = WarpStage<RS, CHUNK>;
     static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(16) float s_w[2][32];  // weight exchange, double buffered
+    __shared__ __align__(16) float s_w[2][(1 + NGL) * XROW];  // weights + NGL geometry terms, double buffered
 
     const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -158,10 +166,12 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
         for (int ps = 0; ps < NPASS; ++ps) {
             const int c = ps * 32 + (int)lane;
 #pragma unroll
-            for (int q = 0; q < 32; ++q) gT[ps][q] = (c < CT4) ? ts[q * TS + c] : 0.f;
+            for (int q = 0; q < 32; ++q) gT[ps][q] = (c < CT4) ? ts[q * TS + c] : ((c < CT4 + NGL) ? 1.0f : 0.f);
         }
         __syncwarp();
     }
+    // which exchanged array this lane sums in the outer-product phase: 0 = weights, 1 + k = geometry term k
+    const uint32_t my_array = ((int)lane >= CT4 && (int)lane < CT4 + NGL) ? (1u + lane - CT4) : 0u;
     Stage stage;
     stage.init(smem_raw);
     const int nrounds = (n_eff + CHUNK - 1) / CHUNK;
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
     const float ddely_dy = 0.5f * (float)p.H;
     const uint32_t w_addr = smem_u32(&s_w[0][0]);
     unsigned parity = 0;
-    float pv[8];          // geometry terms of the last blended entry, not yet reduced across the warp
+    float pv[NB > 0 ? NB : 1];  // geometry terms of the last blended entry still to be reduced by the butterfly
     float* pgrec = nullptr;
     bool pend = false;    // warp-uniform
 
@@ -204,10 +214,14 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             const float2 h1 = lds64(ra + 16);
             // Geometry terms of the PREVIOUS blended entry: their shuffle butterfly (5 dependent levels) is issued
             // here so that its latency overlaps this entry's load -> power -> exp -> alpha chain.
-            if (pend) {
-                WarpTransposeReduce<8, 16>::run(pv, lane);
-                if ((lane & 3u) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), pv[0]);
-                pend = false;
+            if constexpr (NB > 0) {
+                if (pend) {
+                    WarpTransposeReduce<NB, 16>::run(pv, lane);
+                    constexpr int kShift = NB == 8 ? 2 : 3;  // value k ends in lanes k << kShift
+                    if ((lane & ((1u << kShift) - 1u)) == 0u && pv[0] != 0.f)
+                        atomicAdd(pgrec + CT4 + NGL + (lane >> kShift), pv[0]);
+                    pend = false;
+                }
             }
             const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
             const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
@@ -243,27 +257,28 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             const float kdx = ku * dx, kdy = ku * dy;
             const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
             const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
-            pv[0] = mx;
-            pv[1] = my;
-            pv[2] = fabsf(mx);
-            pv[3] = fabsf(my);
-            pv[4] = -0.5f * kdx * dx;
-            pv[5] = -0.5f * kdx * dy;
-            pv[6] = -0.5f * kdy * dy;
-            pv[7] = u;
-            pend = true;
+            const float gv[8] = {mx, my, fabsf(mx), fabsf(my), -0.5f * kdx * dx, -0.5f * kdx * dy, -0.5f * kdy * dy, u};
+#pragma unroll
+            for (int k = NGL; k < 8; ++k) pv[k - NGL] = gv[k];
+#pragma unroll
+            for (int k = 8 - NGL; k < NB; ++k) pv[k] = 0.f;  // butterfly padding
+            pend = NB > 0;
 
-            // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels ----
-            const uint32_t wa = w_addr + parity * 128u;
+            // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels; lanes CT4.. sum the
+            //      first NGL geometry terms the same way ----
+            const uint32_t wa = w_addr + parity * (uint32_t)((1 + NGL) * XROW * 4);
             parity ^= 1u;
             sts32(wa + lane * 4u, w);
+#pragma unroll
+            for (int k = 0; k < NGL; ++k) sts32(wa + (uint32_t)((1 + k) * XROW * 4) + lane * 4u, gv[k]);
             __syncwarp();
+            const uint32_t wl = wa + my_array * (uint32_t)(XROW * 4);
             float cg[NPASS][4];
 #pragma unroll
             for (int ps = 0; ps < NPASS; ++ps) cg[ps][0] = cg[ps][1] = cg[ps][2] = cg[ps][3] = 0.f;
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
-                const float4 wq = lds128(wa + q4 * 16);
+                const float4 wq = lds128(wl + q4 * 16);
 #pragma unroll
                 for (int ps = 0; ps < NPASS; ++ps) {
                     cg[ps][0] += wq.x * gT[ps][4 * q4 + 0];
@@ -277,14 +292,18 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             for (int ps = 0; ps < NPASS; ++ps) {
                 const int c = ps * 32 + (int)lane;
                 const float sum = (cg[ps][0] + cg[ps][1]) + (cg[ps][2] + cg[ps][3]);
-                if (c < p.n_channels && sum != 0.f) atomicAdd(grec + c, sum);
+                // record layout: channel c at c, geometry term k at CT4 + k — i.e. at this lane's own index
+                if ((c < p.n_channels || (c >= CT4 && c < CT4 + NGL)) && sum != 0.f) atomicAdd(grec + c, sum);
             }
             pgrec = grec;  // the geometry terms (pv) are reduced at the top of the next iteration
         }
     }
-    if (pend) {
-        WarpTransposeReduce<8, 16>::run(pv, lane);
-        if ((lane & 3u) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), pv[0]);
+    if constexpr (NB > 0) {
+        if (pend) {
+            WarpTransposeReduce<NB, 16>::run(pv, lane);
+            constexpr int kShift = NB == 8 ? 2 : 3;
+            if ((lane & ((1u << kShift) - 1u)) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + NGL + (lane >> kShift), pv[0]);
+        }
     }
 }
 
