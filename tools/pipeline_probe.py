@@ -15,7 +15,8 @@ from lsx_b200.multiview import GradArena  # noqa: E402
 
 dev = torch.device("cuda:0")
 V = 8
-c, scene, grads, bg, views = bench.build_views("C3", dev, 0, 1, V)
+CFG = sys.argv[1] if len(sys.argv) > 1 else "C3"
+c, scene, grads, bg, views = bench.build_views(CFG, dev, 0, 1, V)
 arena = GradArena.allocate(c["P"], 16, c["F"], 3, dev)
 seq = bench.batch_stepper(ops, views, grads, arena, 1)
 
