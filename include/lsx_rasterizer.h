@@ -163,6 +163,20 @@ LSX_API int lsx_mark_visible(int32_t P, const float* means3D, const float* viewm
 LSX_API int lsx_knn_mean_dist2(int32_t P, const float* points, float* out, lsx_alloc_fn alloc, void* alloc_user,
                        void* stream);
 
+/* ---- next row: plane depth -> depth normal ---------------------------------------------------
+ * Replaces render_normal() -> normal_from_depth_image() -> depth_pcd2normal() (offset == None) of the render wrapper
+ * (field_construction/gaussian_renderer/__init__.py:28-40, field_construction/utils/graphics_utils.py:16-75) together with
+ * the `* rendered_alpha.detach()` of its call site (gaussian_renderer/__init__.py:233-235).
+ *   depth       H*W   plane depth
+ *   alpha       H*W   or NULL: per-pixel factor multiplied into the normal (treated as a constant: no gradient)
+ *   out_normal  3*H*W planar; zero on the one-pixel border
+ * K = [[fx,0,cx],[0,fy,cy],[0,0,1]] as built by Camera.get_calib_matrix_nerf (field_construction/scene/cameras.py:153-156). */
+LSX_API int lsx_depth_normal_forward(int32_t W, int32_t H, float fx, float fy, float cx, float cy, const float* depth,
+                                     const float* alpha, float* out_normal, void* stream);
+/* dL_ddepth (H*W, fully written) from dL_dnormal (3*H*W); same depth / alpha as the forward call. */
+LSX_API int lsx_depth_normal_backward(int32_t W, int32_t H, float fx, float fy, float cx, float cy, const float* depth,
+                                      const float* alpha, const float* dL_dnormal, float* dL_ddepth, void* stream);
+
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 
 /* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the

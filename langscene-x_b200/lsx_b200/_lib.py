@@ -74,6 +74,10 @@ EXPORTS = {
     "lsx_rasterize_backward": (c_int32, [POINTER(BackwardArgs)]),
     "lsx_mark_visible": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_knn_mean_dist2": (c_int32, [c_int32, c_void_p, c_void_p, ALLOC_FN, c_void_p, c_void_p]),
+    "lsx_depth_normal_forward": (c_int32, [c_int32, c_int32, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                           c_void_p]),
+    "lsx_depth_normal_backward": (c_int32, [c_int32, c_int32, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

@@ -1,0 +1,66 @@
+"""Fused pieces of LangScene-X's render wrapper on the C ABI.
+
+`render_normal(viewpoint_cam, depth, ...)` mirrors field_construction/gaussian_renderer/__init__.py:28-40
+(-> field_construction/utils/graphics_utils.py:65-75 normal_from_depth_image -> :42-63 depth_pcd2normal): the normal of
+the surface seen in a (H, W) depth image, (3, H, W), zero on the one-pixel border.  `alpha=` additionally fuses the
+`* rendered_alpha.detach()` of the call site (gaussian_renderer/__init__.py:233-235).  One CUDA kernel each way instead of
+~15 torch kernels and their autograd graph.  No CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _DepthToNormal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, alpha, fx, fy, cx, cy):
+        if not depth.is_cuda:
+            raise RuntimeError("depth must be a CUDA tensor (this operator has no CPU path)")
+        if depth.dim() != 2 or depth.dtype != torch.float32:
+            raise RuntimeError("depth must be a float32 tensor of shape (H, W)")
+        depth = depth.contiguous()
+        H, W = depth.shape
+        if alpha is not None:
+            alpha = alpha.detach().reshape(H, W).to(torch.float32).contiguous()
+        out = torch.empty((3, H, W), dtype=torch.float32, device=depth.device)
+        with torch.cuda.device(depth.device):
+            _lib.check(_lib.load().lsx_depth_normal_forward(W, H, fx, fy, cx, cy, depth.data_ptr(),
+                                                            alpha.data_ptr() if alpha is not None else None, out.data_ptr(),
+                                                            _stream(depth.device)), "depth_normal")
+        ctx.save_for_backward(depth, alpha if alpha is not None else torch.empty(0, device=depth.device))
+        ctx.intr = (fx, fy, cx, cy)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        depth, alpha = ctx.saved_tensors
+        fx, fy, cx, cy = ctx.intr
+        H, W = depth.shape
+        grad_out = grad_out.to(torch.float32).contiguous()
+        g_depth = torch.empty_like(depth)
+        with torch.cuda.device(depth.device):
+            _lib.check(_lib.load().lsx_depth_normal_backward(W, H, fx, fy, cx, cy, depth.data_ptr(),
+                                                             alpha.data_ptr() if alpha.numel() else None, grad_out.data_ptr(),
+                                                             g_depth.data_ptr(), _stream(depth.device)), "depth_normal backward")
+        return g_depth, None, None, None, None, None
+
+
+def depth_to_normal(depth, fx, fy, cx, cy, alpha=None):
+    """normal (3, H, W) of the depth image `depth` (H, W) under K = [[fx,0,cx],[0,fy,cy],[0,0,1]], times `alpha` if given."""
+    return _DepthToNormal.apply(depth, alpha, float(fx), float(fy), float(cx), float(cy))
+
+
+def render_normal(viewpoint_cam, depth, offset=None, normal=None, scale=1, alpha=None):
+    """Drop-in for the reference's render_normal (same positional arguments).  `viewpoint_cam` needs Fx, Fy, Cx, Cy (as used
+    by Camera.get_calib_matrix_nerf, field_construction/scene/cameras.py:153-156).  The reference's optional sampling
+    `offset` and the sub-sampling `scale` have no call site in the training loop and are not supported here."""
+    if offset is not None or scale != 1:
+        raise NotImplementedError("render_normal: offset / scale != 1 are not supported by the fused kernel")
+    return depth_to_normal(depth, viewpoint_cam.Fx / scale, viewpoint_cam.Fy / scale, viewpoint_cam.Cx / scale,
+                           viewpoint_cam.Cy / scale, alpha=alpha)
