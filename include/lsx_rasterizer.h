@@ -201,6 +201,7 @@ typedef struct lsx_scratch_layout {
     /* binning buffer, R rows */
     size_t point_list;     /* u32[R] sorted Gaussian indices */
     size_t binning_bytes;
+    size_t masks;          /* u8[R]  sub-tile footprint mask per list entry (binning buffer) */
 } lsx_scratch_layout;
 
 LSX_API int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,

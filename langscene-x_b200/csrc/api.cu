@@ -177,7 +177,8 @@ BinningScratch carve_binning(char* base, int R, lsx_scratch_layout* lay) {
     const size_t r = (size_t)(R > 0 ? R : 0);
     size_t o0;
     s.point_list = c.take<uint32_t>(r, &o0);
-    s.masks = c.take<uint8_t>(r);
+    size_t om = 0;
+    s.masks = c.take<uint8_t>(r, &om);
     s.vals_alt = c.take<uint32_t>(r);
     s.tile_keys[0] = c.take<uint32_t>(r);
     s.tile_keys[1] = c.take<uint32_t>(r);
@@ -186,6 +187,7 @@ BinningScratch carve_binning(char* base, int R, lsx_scratch_layout* lay) {
     if (lay) {
         lay->point_list = o0;
         lay->binning_bytes = s.bytes;
+        lay->masks = om;
     }
     return s;
 }

@@ -64,7 +64,7 @@ class ScratchLayout(ctypes.Structure):
         ("conic_opacity", c_size_t), ("rgb", c_size_t), ("tiles_touched", c_size_t), ("records", c_size_t),
         ("record_stride", c_int32), ("geom_bytes", c_size_t),
         ("final_T", c_size_t), ("n_contrib", c_size_t), ("ranges", c_size_t), ("image_bytes", c_size_t),
-        ("point_list", c_size_t), ("binning_bytes", c_size_t),
+        ("point_list", c_size_t), ("binning_bytes", c_size_t), ("masks", c_size_t),
     ]
 
 

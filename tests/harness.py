@@ -100,6 +100,7 @@ def parse_new_buffers(geom, binning, img, P, R, W, H, n_blend):
     out["tiles_touched"] = _view(geom, lay.tiles_touched, P, torch.int32)
     if R > 0:
         out["point_list"] = _view(binning, lay.point_list, R, torch.int32)
+        out["masks"] = _view(binning, lay.masks, R, torch.uint8)
         keys = torch.empty(R, dtype=torch.int64, device=geom.device)
         _lib.check(lib.lsx_debug_sorted_keys(P, W, H, R, n_blend, geom.data_ptr(), binning.data_ptr(), img.data_ptr(),
                                              keys.data_ptr(), torch.cuda.current_stream().cuda_stream), "debug keys")

@@ -372,6 +372,53 @@ def test_backward_accumulates_into_caller_buffers():
             assert hz.rel_err(v, expect[gname].reshape(v.shape)) < 2e-5, gname
 
 
+@pytest.mark.parametrize("s_med,aniso,opac_shift,scale_mod,seed", [
+    (0.02, 2.5, 0.0, 1.0, 41), (0.003, 1.0, -3.5, 1.0, 42), (0.05, 0.5, 3.0, 2.0, 43), (0.01, 3.0, -1.0, 0.5, 44),
+])
+def test_footprint_masks_against_brute_force(s_med, aniso, opac_shift, scale_mod, seed):
+    """Direct property test of cull.cu: for every (tile-list entry, 8x4 block) whose mask bit is CLEAR, no pixel of that
+    block may pass the reference's blend test (power <= 0 and min(0.99, opacity * exp(power)) >= 1/255), evaluated here
+    per pixel with torch in fp32 and fp64.  Also reports how much the masks remove."""
+    P, W, H, F = 6_000, 208, 144, 3
+    scene, cam, _ = _scene(P, W, H, F, seed=seed, s_med=s_med)
+    g = torch.Generator().manual_seed(seed)
+    scene.scales = (scene.scales * torch.exp(aniso * torch.randn(P, 3, generator=g)).to(scene.scales.device)).contiguous()
+    scene.opacities = torch.sigmoid(torch.logit(scene.opacities.clamp(1e-4, 1 - 1e-4)) + opac_shift).contiguous()
+    fargs = hz.native_forward_args(scene, cam, torch.zeros(3, device="cuda:0"), F, scale_modifier=scale_mod)
+    fwd = dict(zip(hz.FWD_NAMES, _new().rasterize_gaussians(*fargs)))
+    R = fwd["num_rendered"]
+    assert R > 0
+    buf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H, 3 + F + 3 + 5)
+    ids = buf["point_list"].long()
+    masks = buf["masks"].long()
+    ranges = buf["ranges"].long()
+    gx = (W + 15) // 16
+    tile_of = torch.repeat_interleave(torch.arange(ranges.shape[0], device="cuda:0"), (ranges[:, 1] - ranges[:, 0]))
+    assert tile_of.numel() == R
+    mean = buf["means2D"][ids]                      # (R, 2)
+    co = buf["conic_opacity"][ids]                  # (R, 4)
+    tx0, ty0 = (tile_of % gx) * 16, (tile_of // gx) * 16
+    violations, kept, total = 0, 0, 0
+    for dtype in (torch.float32, torch.float64):
+        for w in range(8):
+            xs = (tx0 + (w & 1) * 8).view(-1, 1, 1) + torch.arange(8, device="cuda:0").view(1, 1, 8)
+            ys = (ty0 + (w >> 1) * 4).view(-1, 1, 1) + torch.arange(4, device="cuda:0").view(1, 4, 1)
+            dx = mean[:, 0].to(dtype).view(-1, 1, 1) - xs.to(dtype)
+            dy = mean[:, 1].to(dtype).view(-1, 1, 1) - ys.to(dtype)
+            a, b, c, o = (co[:, k].to(dtype).view(-1, 1, 1) for k in range(4))
+            power = -0.5 * (a * dx * dx + c * dy * dy) - b * dx * dy
+            alpha = torch.clamp(o * torch.exp(power), max=0.99)
+            blends = ((power <= 0) & (alpha >= 1.0 / 255.0) & (xs < W) & (ys < H)).flatten(1).any(1)
+            bit = ((masks >> w) & 1).bool()
+            violations += int((blends & ~bit).sum())
+            if dtype == torch.float32:
+                kept += int(bit.sum())
+                total += R
+    assert violations == 0, f"{violations} (block, entry) pairs would blend but are masked out"
+    assert kept < total          # the masks do remove work on these scenes
+    print(f"masks keep {kept / total:.1%} of the (block, entry) pairs")
+
+
 def test_no_memory_growth_without_cyclic_gc():
     """Scratch, outputs and gradients must be released by reference counting alone (a ctypes callback capturing its
     owner once kept every call's ~400 B/Gaussian scratch alive until the cyclic collector ran)."""
