@@ -639,17 +639,29 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// The opt-in dynamic shared-memory limit is a per-device attribute of the function: remember what has been set for
+// (kernel slot, device) so that a process driving several GPUs configures each of them (benign race: monotone maximum).
+static cudaError_t ensure_dynamic_smem(const void* func, size_t bytes, int slot) {
+    static size_t configured[2][64] = {};
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int d = dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+    if (dev > 63 || bytes > configured[slot][d]) {
+        e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) configured[slot][d] = bytes;
+    }
+    return e;
+}
+
 int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
     const int n_sh = p.M * 3;
     const int sh_stride = p.shs ? padded_row(n_sh) : 0;
     const size_t smem = ((size_t)((kPreFwdThreads * sh_stride + 3) & ~3) + (size_t)kPreFwdThreads * record_tile_row(p.rec_stride)) *
                         sizeof(float);
-    static size_t configured = 0;  // benign race: monotone maximum
-    if (smem > configured) {
-        LSX_CUDA_OK(cudaFuncSetAttribute(preprocess_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel), smem, 0));
     preprocess_fwd_kernel<<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
@@ -658,11 +670,7 @@ int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, boo
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
     const size_t smem = (size_t)kPreBwdThreads * ((p.shs ? padded_row(p.M * 3) : 0) + padded_row(p.grad_stride)) * sizeof(float);
-    static size_t configured = 0;  // benign race: monotone maximum
-    if (smem > configured) {
-        LSX_CUDA_OK(cudaFuncSetAttribute(preprocess_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel), smem, 1));
     preprocess_bwd_kernel<<<ceil_div(p.P, kPreBwdThreads), kPreBwdThreads, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;

@@ -218,10 +218,11 @@ def test_against_golden_vectors(path):
             assert hz.rel_err(bwd[k], ref) < BWD_TOL, k
 
 
-def test_against_cpu_oracle():
+@pytest.mark.parametrize("F", [3, 8, 29])   # 29 -> 40 blended channels: the widest supported record, two channel passes in
+def test_against_cpu_oracle(F):              # the backward, > 48 KB of opt-in shared memory in the preprocess kernels
     from oracle import oracle as orc
     from lsx_b200.synthetic import make_all_map
-    P, W, H, F = 4000, 128, 96, 3
+    P, W, H = 4000, 128, 96
     scene, cam, grads = _scene(P, W, H, F, seed=21)
     bg = torch.tensor([0.2, 0.2, 0.2], device="cuda:0")
     am = make_all_map(scene, cam)
@@ -236,7 +237,7 @@ def test_against_cpu_oracle():
                                 c(grads["all_map"]), c(grads["plane_depth"]))
     assert int((o["radii"] != c(fwd["radii"])).sum()) <= 2
     same = (o["n_contrib"].reshape(H, W) == c(hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P,
-                                                                   fwd["num_rendered"], W, H, 14)["n_contrib"]).reshape(H, W))
+                                                                   fwd["num_rendered"], W, H, 3 + F + 3 + 5)["n_contrib"]).reshape(H, W))
     assert same.mean() > 0.99
     for k in ["color", "language_feature", "instance_feature", "all_map"]:
         a, b = c(fwd[k])[:, same], o[k][:, same]
@@ -417,6 +418,14 @@ def test_footprint_masks_against_brute_force(s_med, aniso, opac_shift, scale_mod
     assert violations == 0, f"{violations} (block, entry) pairs would blend but are masked out"
     assert kept < total          # the masks do remove work on these scenes
     print(f"masks keep {kept / total:.1%} of the (block, entry) pairs")
+
+
+def test_too_many_channels_is_an_error():
+    ops = _new()
+    scene, cam, grads = _scene(100, 64, 48, 30, seed=1)        # 3 + 30 + 3 + 5 = 41 > LSX_MAX_BLEND_CHANNELS
+    fargs = hz.native_forward_args(scene, cam, torch.zeros(3, device="cuda:0"), 30)
+    with pytest.raises(RuntimeError, match="blended channels"):
+        ops.rasterize_gaussians(*fargs)
 
 
 def test_no_memory_growth_without_cyclic_gc():
