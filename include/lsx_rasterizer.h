@@ -177,6 +177,20 @@ LSX_API int lsx_depth_normal_forward(int32_t W, int32_t H, float fx, float fy, f
 LSX_API int lsx_depth_normal_backward(int32_t W, int32_t H, float fx, float fy, float cx, float cy, const float* depth,
                                       const float* alpha, const float* dL_dnormal, float* dL_ddepth, void* stream);
 
+/* ---- next row: fused L1 + SSIM image loss ------------------------------------------------------
+ * Replaces l1_loss and ssim (11x11 Gaussian window, sigma 1.5, zero padding; field_construction/utils/loss_utils.py:20-75)
+ * as combined at field_construction/gaussian_field.py:238-246.  Images are planar C*H*W fp32.
+ * forward : writes three derivative maps (3*C*H*W floats, consumed by backward) and per-block partial sums
+ *           partial[0..nblk) = sums of the SSIM map, partial[nblk..2 nblk) = sums of |img1 - img2|, nblk =
+ *           lsx_image_loss_num_blocks(C,H,W); the caller adds them up (deterministic) and divides by C*H*W.
+ * backward: dL_dimg1 = k_ssim * d(sum of SSIM map)/d(img1) + k_l1 * sign(img1 - img2)   (fully written);
+ *           for loss = (1-l) * mean|.| + l * (1 - mean ssim):  k_ssim = -l * g / (C*H*W), k_l1 = (1-l) * g / (C*H*W). */
+LSX_API int64_t lsx_image_loss_num_blocks(int32_t C, int32_t H, int32_t W);
+LSX_API int lsx_image_loss_forward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, float* dmaps,
+                                   float* partial, void* stream);
+LSX_API int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, const float* dmaps,
+                                    float k_ssim, float k_l1, float* dL_dimg1, void* stream);
+
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 
 /* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the

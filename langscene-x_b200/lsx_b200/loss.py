@@ -1,0 +1,73 @@
+"""Fused image losses of LangScene-X's training loop on the C ABI.
+
+  ssim(img1, img2)                  drop-in for field_construction/utils/loss_utils.py:37-46 (11x11 window, size_average)
+  image_loss(image, gt, lambda_)    (1 - lambda_) * l1_loss(image, gt) + lambda_ * (1 - ssim(image, gt)), the combination at
+                                    field_construction/gaussian_field.py:238-246, one kernel forward and one backward;
+                                    returns (loss, l1, ssim_value) so that the loop can keep logging both terms.
+Gradients flow to the FIRST image only (the ground-truth image never requires grad in the reference).  No CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_pair(img1, img2):
+    if not (img1.is_cuda and img2.is_cuda):
+        raise RuntimeError("images must be CUDA tensors (this operator has no CPU path)")
+    if img1.shape != img2.shape or img1.dim() != 3:
+        raise RuntimeError("images must both have shape (C, H, W)")
+    if img1.dtype != torch.float32 or img2.dtype != torch.float32:
+        raise RuntimeError("images must be float32")
+
+
+class _ImageLoss(torch.autograd.Function):
+    """returns (mean ssim, mean |x - y|); backward takes the two upstream scalars."""
+
+    @staticmethod
+    def forward(ctx, img1, img2):
+        _check_pair(img1, img2)
+        if img2.requires_grad:
+            raise RuntimeError("the second image is treated as ground truth: it must not require grad")
+        img1c, img2c = img1.contiguous(), img2.contiguous()
+        C, H, W = img1c.shape
+        lib = _lib.load()
+        nblk = int(lib.lsx_image_loss_num_blocks(C, H, W))
+        dmaps = torch.empty((3, C, H, W), dtype=torch.float32, device=img1.device)
+        partial = torch.empty((2, nblk), dtype=torch.float32, device=img1.device)
+        with torch.cuda.device(img1.device):
+            _lib.check(lib.lsx_image_loss_forward(C, H, W, img1c.data_ptr(), img2c.data_ptr(), dmaps.data_ptr(),
+                                                  partial.data_ptr(), _stream(img1.device)), "image_loss")
+        sums = partial.sum(dim=1) / float(C * H * W)
+        ctx.save_for_backward(img1c, img2c, dmaps)
+        return sums[0], sums[1]
+
+    @staticmethod
+    def backward(ctx, g_ssim, g_l1):
+        img1, img2, dmaps = ctx.saved_tensors
+        C, H, W = img1.shape
+        n = float(C * H * W)
+        k_ssim = 0.0 if g_ssim is None else float(g_ssim) / n     # one host read of two scalars per backward
+        k_l1 = 0.0 if g_l1 is None else float(g_l1) / n
+        g = torch.empty_like(img1)
+        with torch.cuda.device(img1.device):
+            _lib.check(_lib.load().lsx_image_loss_backward(C, H, W, img1.data_ptr(), img2.data_ptr(), dmaps.data_ptr(),
+                                                           k_ssim, k_l1, g.data_ptr(), _stream(img1.device)),
+                       "image_loss backward")
+        return g, None
+
+
+def ssim(img1, img2, window_size=11, size_average=True):
+    if window_size != 11 or not size_average:
+        raise NotImplementedError("the fused kernel implements the 11x11, size_average=True case used by the training loop")
+    return _ImageLoss.apply(img1, img2)[0]
+
+
+def image_loss(image, gt, lambda_dssim):
+    s, l1 = _ImageLoss.apply(image, gt)
+    return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - s), l1, s
