@@ -485,6 +485,18 @@ def test_headline_size_properties():
         _compare_all(fargs, grads, F, P, W, H, 27)
 
 
+@pytest.mark.parametrize("P,W,H,F,s_med,yaw", [
+    (500_000, 720, 480, 3, 0.006, -15.0),      # BASELINE config 4: LangScene-X's own frame size, first view of the arc
+    (5_000_000, 1920, 1080, 16, 0.006, 12.0),  # BASELINE config 5 (one view): 26 M list entries, the long-sort path
+])
+def test_large_configs_match_reference(P, W, H, F, s_med, yaw):
+    if hz.ref_rast_for(F) is None:
+        pytest.skip("oracle/_ref not built")
+    scene, cam, grads = _scene(P, W, H, F, seed=4, yaw=yaw, s_med=s_med)
+    fargs = hz.native_forward_args(scene, cam, torch.zeros(3, device="cuda:0"), F)
+    _compare_all(fargs, grads, F, P, W, H, 3 + F + 3 + 5)
+
+
 def test_knn_matches_reference_and_golden():
     from simple_knn._C import distCUDA2
     dev = "cuda:0"
