@@ -191,6 +191,17 @@ LSX_API int lsx_image_loss_forward(int32_t C, int32_t H, int32_t W, const float*
 LSX_API int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, const float* dmaps,
                                     float k_ssim, float k_l1, float* dL_dimg1, void* stream);
 
+/* Adam step over flat fp32 arenas (parameters, gradients, both moments share one layout of n elements).  Replaces
+ * torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() of the reference (field_construction/scene/gaussian_model.py:313-328,
+ * field_construction/gaussian_field.py:537-543): default betas, no weight decay, no amsgrad, one learning rate per group.
+ * group_begin_host[0..n_groups] are ascending element offsets (multiples of 4; elements outside [begin[0], begin[n_groups])
+ * get lr 0 but their moments are still updated), group_lr_host[0..n_groups) the learning rates; both are HOST arrays.
+ * `step` is the 1-based step count used for the bias corrections. */
+#define LSX_ADAM_MAX_GROUPS 16
+LSX_API int lsx_arena_adam_step(int64_t n, int32_t n_groups, const int64_t* group_begin_host, const float* group_lr_host,
+                                int32_t step, float beta1, float beta2, float eps, float* params, const float* grads,
+                                float* exp_avg, float* exp_avg_sq, void* stream);
+
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 
 /* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the

@@ -82,6 +82,8 @@ EXPORTS = {
     "lsx_image_loss_forward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_image_loss_backward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
                                           c_void_p]),
+    "lsx_arena_adam_step": (c_int32, [ctypes.c_int64, c_int32, POINTER(ctypes.c_int64), POINTER(c_float), c_int32, c_float, c_float,
+                                      c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

@@ -36,6 +36,7 @@ class GradArena:
     """Flat accumulation buffer for the parameter gradients of P Gaussians."""
     flat: torch.Tensor
     views: Dict[str, torch.Tensor]
+    offsets: Dict[str, Tuple[int, int]] = None   # group name -> (first element, element count) inside `flat`
 
     @staticmethod
     def allocate(P: int, M: int, F: int, Fi: int, device) -> "GradArena":
@@ -48,7 +49,7 @@ class GradArena:
         flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
         views = {name: flat[o:o + n].view(P, widths[name]) if widths[name] else flat[o:o]
                  for name, (o, n) in offs.items()}
-        return GradArena(flat, views)
+        return GradArena(flat, views, offs)
 
     def zero_(self):
         self.flat.zero_()
