@@ -191,6 +191,23 @@ LSX_API int lsx_image_loss_forward(int32_t C, int32_t H, int32_t W, const float*
 LSX_API int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, const float* dmaps,
                                     float k_ssim, float k_l1, float* dL_dimg1, void* stream);
 
+/* ---- next row (per-Gaussian half of the render wrapper) -----------------------------------------------------
+ * forward : scales = exp(scaling_raw) (P*3), rotations = normalize(rotation_raw) (P*4), opacity = sigmoid(opacity_raw) (P),
+ *           all_map (P*5) = [plane normal in camera space, 1, |<normal, camera-space position>|], the plane normal being the
+ *           rotation-matrix column of the smallest scale, flipped towards the camera
+ *           (field_construction/scene/gaussian_model.py:53-61,193-236; field_construction/gaussian_renderer/__init__.py:188-196).
+ * backward: gradients w.r.t. the raw parameters from the gradients the rasterizer returns for scales / rotations / opacities /
+ *           all_map (any of them may be NULL = zero); dL_dmeans3D (may be NULL) is added to the position gradient.
+ * viewmatrix_host (16 floats, the reference's world_view_transform in its own memory order) and campos_host (3) are HOST arrays. */
+LSX_API int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+                                      const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                      float* scales, float* rotations, float* opacity, float* all_map, void* stream);
+LSX_API int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+                                       const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                       const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
+                                       const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
+                                       float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw, void* stream);
+
 /* Adam step over flat fp32 arenas (parameters, gradients, both moments share one layout of n elements).  Replaces
  * torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() of the reference (field_construction/scene/gaussian_model.py:313-328,
  * field_construction/gaussian_field.py:537-543): default betas, no weight decay, no amsgrad, one learning rate per group.

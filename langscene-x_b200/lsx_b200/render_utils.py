@@ -64,3 +64,59 @@ def render_normal(viewpoint_cam, depth, offset=None, normal=None, scale=1, alpha
         raise NotImplementedError("render_normal: offset / scale != 1 are not supported by the fused kernel")
     return depth_to_normal(depth, viewpoint_cam.Fx / scale, viewpoint_cam.Fy / scale, viewpoint_cam.Cx / scale,
                            viewpoint_cam.Cy / scale, alpha=alpha)
+
+
+class _GaussianHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, scaling_raw, rotation_raw, opacity_raw, viewmatrix, campos):
+        for name, t in (("xyz", xyz), ("scaling", scaling_raw), ("rotation", rotation_raw), ("opacity", opacity_raw)):
+            if not t.is_cuda:
+                raise RuntimeError(f"{name} must be a CUDA tensor (this operator has no CPU path)")
+            if t.dtype != torch.float32:
+                raise RuntimeError(f"{name} must be float32")
+        P = int(xyz.shape[0])
+        if xyz.shape != (P, 3) or scaling_raw.shape != (P, 3) or rotation_raw.shape != (P, 4) or opacity_raw.numel() != P:
+            raise RuntimeError("expected xyz (P,3), scaling (P,3), rotation (P,4), opacity (P,1)")
+        xyz, scaling_raw, rotation_raw, opacity_raw = (t.contiguous() for t in (xyz, scaling_raw, rotation_raw, opacity_raw))
+        view = (ctypes.c_float * 16)(*viewmatrix.detach().reshape(-1).tolist())   # 19 floats host side: tiny D2H if on GPU
+        cam = (ctypes.c_float * 3)(*campos.detach().reshape(-1).tolist())
+        dev = xyz.device
+        opts = dict(dtype=torch.float32, device=dev)
+        scales, rotations = torch.empty((P, 3), **opts), torch.empty((P, 4), **opts)
+        opacity, all_map = torch.empty((P, 1), **opts), torch.empty((P, 5), **opts)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().lsx_gaussian_head_forward(P, view, cam, xyz.data_ptr(), scaling_raw.data_ptr(),
+                                                             rotation_raw.data_ptr(), opacity_raw.data_ptr(), scales.data_ptr(),
+                                                             rotations.data_ptr(), opacity.data_ptr(), all_map.data_ptr(),
+                                                             _stream(dev)), "gaussian_head")
+        ctx.save_for_backward(xyz, scaling_raw, rotation_raw, opacity_raw)
+        ctx.cam = (view, cam)
+        return scales, rotations, opacity, all_map
+
+    @staticmethod
+    def backward(ctx, g_scales, g_rotations, g_opacity, g_all_map):
+        xyz, scaling_raw, rotation_raw, opacity_raw = ctx.saved_tensors
+        view, cam = ctx.cam
+        P, dev = int(xyz.shape[0]), xyz.device
+        ptr = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        g_scales, g_rotations, g_opacity, g_all_map = (ptr(t) for t in (g_scales, g_rotations, g_opacity, g_all_map))
+        dp = lambda t: None if t is None else t.data_ptr()
+        opts = dict(dtype=torch.float32, device=dev)
+        g_xyz, g_s, g_r = torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 4), **opts)
+        g_o = torch.empty(opacity_raw.shape, **opts)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().lsx_gaussian_head_backward(P, view, cam, xyz.data_ptr(), scaling_raw.data_ptr(),
+                                                              rotation_raw.data_ptr(), opacity_raw.data_ptr(), dp(g_scales),
+                                                              dp(g_rotations), dp(g_opacity), dp(g_all_map), None,
+                                                              g_xyz.data_ptr(), g_s.data_ptr(), g_r.data_ptr(), g_o.data_ptr(),
+                                                              _stream(dev)), "gaussian_head backward")
+        return g_xyz, g_s, g_r, g_o, None, None
+
+
+def gaussian_head(xyz, scaling_raw, rotation_raw, opacity_raw, viewmatrix, campos):
+    """(scales, rotations, opacity, all_map) for the rasterizer from the raw Gaussian parameters and one camera: the fused
+    form of get_scaling / get_rotation / get_opacity / get_normal and of the all_map lines of render()
+    (field_construction/scene/gaussian_model.py:193-236, field_construction/gaussian_renderer/__init__.py:188-196).
+    The position gradient returned for `xyz` is only the part that flows through all_map; the rasterizer's own
+    dL/dmeans3D reaches `xyz` through autograd as usual."""
+    return _GaussianHead.apply(xyz, scaling_raw, rotation_raw, opacity_raw, viewmatrix, campos)

@@ -69,7 +69,7 @@ def test_cuda_matches_restatement_at_1080p_and_errors():
     d = img.cuda().requires_grad_(True)
     loss, l1, s = image_loss(d, gt.cuda(), 0.2)
     loss.backward()
-    assert abs(float(loss) - float(want)) < 1e-5
+    assert abs(float(loss.detach()) - float(want.detach())) < 1e-5
     assert _rel(d.grad.cpu(), a.grad) < 1e-4
     with pytest.raises(RuntimeError):
         ssim(img, gt)                                   # CPU tensors: no fallback
