@@ -183,13 +183,13 @@ LSX_API int lsx_depth_normal_backward(int32_t W, int32_t H, float fx, float fy, 
  * forward : writes three derivative maps (3*C*H*W floats, consumed by backward) and per-block partial sums
  *           partial[0..nblk) = sums of the SSIM map, partial[nblk..2 nblk) = sums of |img1 - img2|, nblk =
  *           lsx_image_loss_num_blocks(C,H,W); the caller adds them up (deterministic) and divides by C*H*W.
- * backward: dL_dimg1 = k_ssim * d(sum of SSIM map)/d(img1) + k_l1 * sign(img1 - img2)   (fully written);
- *           for loss = (1-l) * mean|.| + l * (1 - mean ssim):  k_ssim = -l * g / (C*H*W), k_l1 = (1-l) * g / (C*H*W). */
+ * backward: dL_dssim_mean / dL_dl1_mean are DEVICE scalars (may be NULL = 0): the upstream gradients of the two means, e.g.
+ *           -l * g and (1-l) * g for loss = (1-l) * mean|.| + l * (1 - mean ssim); dL_dimg1 (C*H*W) is fully written. */
 LSX_API int64_t lsx_image_loss_num_blocks(int32_t C, int32_t H, int32_t W);
 LSX_API int lsx_image_loss_forward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, float* dmaps,
                                    float* partial, void* stream);
 LSX_API int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, const float* dmaps,
-                                    float k_ssim, float k_l1, float* dL_dimg1, void* stream);
+                                    const float* dL_dssim_mean, const float* dL_dl1_mean, float* dL_dimg1, void* stream);
 
 /* ---- next row (per-Gaussian half of the render wrapper) -----------------------------------------------------
  * forward : scales = exp(scaling_raw) (P*3), rotations = normalize(rotation_raw) (P*4), opacity = sigmoid(opacity_raw) (P),
@@ -198,11 +198,12 @@ LSX_API int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float
  *           (field_construction/scene/gaussian_model.py:53-61,193-236; field_construction/gaussian_renderer/__init__.py:188-196).
  * backward: gradients w.r.t. the raw parameters from the gradients the rasterizer returns for scales / rotations / opacities /
  *           all_map (any of them may be NULL = zero); dL_dmeans3D (may be NULL) is added to the position gradient.
- * viewmatrix_host (16 floats, the reference's world_view_transform in its own memory order) and campos_host (3) are HOST arrays. */
-LSX_API int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+ * viewmatrix (16 floats, the reference's world_view_transform in its own memory order) and campos (3) are DEVICE arrays, as in
+ * lsx_forward_args. */
+LSX_API int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
                                       const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
                                       float* scales, float* rotations, float* opacity, float* all_map, void* stream);
-LSX_API int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+LSX_API int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
                                        const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
                                        const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
                                        const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,

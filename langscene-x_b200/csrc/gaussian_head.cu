@@ -64,7 +64,17 @@ __device__ __forceinline__ HeadFrame head_frame(const HeadCam& c, const float* x
     return f;
 }
 
-__global__ void __launch_bounds__(256) gaussian_head_fwd_kernel(const int P, const HeadCam c, const float* __restrict__ xyz,
+__device__ __forceinline__ HeadCam load_cam(const float* __restrict__ view, const float* __restrict__ campos) {
+    HeadCam c;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.v[k] = __ldg(view + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c.cam[k] = __ldg(campos + k);
+    return c;
+}
+
+__global__ void __launch_bounds__(256) gaussian_head_fwd_kernel(const int P, const float* __restrict__ view,
+                                                                const float* __restrict__ campos, const float* __restrict__ xyz,
                                                                 const float* __restrict__ scaling_raw,
                                                                 const float* __restrict__ rotation_raw,
                                                                 const float* __restrict__ opacity_raw, float* __restrict__ scales,
@@ -72,6 +82,7 @@ __global__ void __launch_bounds__(256) gaussian_head_fwd_kernel(const int P, con
                                                                 float* __restrict__ all_map) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    const HeadCam c = load_cam(view, campos);
     const float x[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     const float s[3] = {scaling_raw[3 * i], scaling_raw[3 * i + 1], scaling_raw[3 * i + 2]};
     const HeadFrame f = head_frame(c, x, s, reinterpret_cast<const float4*>(rotation_raw)[i], opacity_raw[i]);
@@ -87,13 +98,14 @@ __global__ void __launch_bounds__(256) gaussian_head_fwd_kernel(const int P, con
 }
 
 __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
-    const int P, const HeadCam c, const float* __restrict__ xyz, const float* __restrict__ scaling_raw,
+    const int P, const float* __restrict__ view, const float* __restrict__ campos, const float* __restrict__ xyz, const float* __restrict__ scaling_raw,
     const float* __restrict__ rotation_raw, const float* __restrict__ opacity_raw, const float* __restrict__ g_scales,
     const float* __restrict__ g_rotations, const float* __restrict__ g_opacity, const float* __restrict__ g_all_map,
     const float* __restrict__ g_means3D, float* __restrict__ g_xyz, float* __restrict__ g_scaling_raw,
     float* __restrict__ g_rotation_raw, float* __restrict__ g_opacity_raw) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    const HeadCam c = load_cam(view, campos);
     const float x[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     const float s[3] = {scaling_raw[3 * i], scaling_raw[3 * i + 1], scaling_raw[3 * i + 2]};
     const float4 qraw = reinterpret_cast<const float4*>(rotation_raw)[i];
@@ -164,40 +176,33 @@ __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
     reinterpret_cast<float4*>(g_rotation_raw)[i] = out;
 }
 
-HeadCam make_cam(const float* view_host, const float* campos_host) {
-    HeadCam c;
-    for (int k = 0; k < 16; ++k) c.v[k] = view_host[k];
-    for (int k = 0; k < 3; ++k) c.cam[k] = campos_host[k];
-    return c;
-}
-
 }  // namespace
 }  // namespace lsx
 
 using namespace lsx;
 
-extern "C" int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+extern "C" int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
                                          const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
                                          float* scales, float* rotations, float* opacity, float* all_map, void* stream_) {
-    if (P < 0 || !viewmatrix_host || !campos_host ||
+    if (P < 0 || !viewmatrix || !campos ||
         (P > 0 && (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !scales || !rotations || !opacity || !all_map))) {
         set_error("lsx_gaussian_head_forward: bad arguments");
         return -1;
     }
     if (P == 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    gaussian_head_fwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, make_cam(viewmatrix_host, campos_host), xyz, scaling_raw,
-                                                                   rotation_raw, opacity_raw, scales, rotations, opacity, all_map);
+    gaussian_head_fwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw,
+                                                                   opacity_raw, scales, rotations, opacity, all_map);
     LSX_KERNEL_OK(stream, false);
     return 0;
 }
 
-extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix_host, const float* campos_host, const float* xyz,
+extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
                                           const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
                                           const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
                                           const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
                                           float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw, void* stream_) {
-    if (P < 0 || !viewmatrix_host || !campos_host ||
+    if (P < 0 || !viewmatrix || !campos ||
         (P > 0 && (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !dL_dxyz || !dL_dscaling_raw || !dL_drotation_raw ||
                    !dL_dopacity_raw))) {
         set_error("lsx_gaussian_head_backward: bad arguments");
@@ -205,8 +210,8 @@ extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix_hos
     }
     if (P == 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    gaussian_head_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, make_cam(viewmatrix_host, campos_host), xyz, scaling_raw,
-                                                                   rotation_raw, opacity_raw, dL_dscales, dL_drotations,
+    gaussian_head_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw,
+                                                                   opacity_raw, dL_dscales, dL_drotations,
                                                                    dL_dopacity, dL_dall_map, dL_dmeans3D, dL_dxyz, dL_dscaling_raw,
                                                                    dL_drotation_raw, dL_dopacity_raw);
     LSX_KERNEL_OK(stream, false);

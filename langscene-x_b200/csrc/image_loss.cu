@@ -108,8 +108,11 @@ __global__ void __launch_bounds__(256) ssim_l1_fwd_kernel(const int C, const int
 // dL/dimg1 = k_ssim * [ w*(d_mu1) + 2 x w*(d_ex2) + y w*(d_exy) ] + k_l1 * sign(x - y)
 __global__ void __launch_bounds__(256) ssim_l1_bwd_kernel(const int C, const int H, const int W, const Window win,
                                                           const float* __restrict__ img1, const float* __restrict__ img2,
-                                                          const float* __restrict__ dmaps, const float k_ssim, const float k_l1,
+                                                          const float* __restrict__ dmaps, const float* __restrict__ g_ssim,
+                                                          const float* __restrict__ g_l1, const float inv_n,
                                                           float* __restrict__ g_img1) {
+    // upstream gradients of the two means are read from device memory: no host round trip in the autograd backward
+    const float k_ssim = g_ssim ? __ldg(g_ssim) * inv_n : 0.f, k_l1 = g_l1 ? __ldg(g_l1) * inv_n : 0.f;
     __shared__ float s[3][kTileI][kTileI + 1];
     __shared__ float h[3][kTileI][kTileO + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -189,14 +192,15 @@ extern "C" int lsx_image_loss_forward(int32_t C, int32_t H, int32_t W, const flo
 }
 
 extern "C" int lsx_image_loss_backward(int32_t C, int32_t H, int32_t W, const float* img1, const float* img2, const float* dmaps,
-                                       float k_ssim, float k_l1, float* dL_dimg1, void* stream_) {
+                                       const float* dL_dssim_mean, const float* dL_dl1_mean, float* dL_dimg1, void* stream_) {
     if (C <= 0 || H <= 0 || W <= 0 || C > 65535 || !img1 || !img2 || !dmaps || !dL_dimg1) {
         set_error("lsx_image_loss_backward: bad arguments");
         return -1;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const dim3 grid((unsigned)ceil_div(W, kTileO), (unsigned)ceil_div(H, kTileO), (unsigned)C);
-    ssim_l1_bwd_kernel<<<grid, 256, 0, stream>>>(C, H, W, make_window(), img1, img2, dmaps, k_ssim, k_l1, dL_dimg1);
+    ssim_l1_bwd_kernel<<<grid, 256, 0, stream>>>(C, H, W, make_window(), img1, img2, dmaps, dL_dssim_mean, dL_dl1_mean,
+                                                 1.0f / ((float)C * (float)H * (float)W), dL_dimg1);
     LSX_KERNEL_OK(stream, false);
     return 0;
 }

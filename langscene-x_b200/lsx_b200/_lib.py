@@ -80,12 +80,12 @@ EXPORTS = {
                                             c_void_p, c_void_p]),
     "lsx_image_loss_num_blocks": (ctypes.c_int64, [c_int32, c_int32, c_int32]),
     "lsx_image_loss_forward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lsx_image_loss_backward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_float, c_float, c_void_p,
+    "lsx_image_loss_backward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p]),
     "lsx_arena_adam_step": (c_int32, [ctypes.c_int64, c_int32, POINTER(ctypes.c_int64), POINTER(c_float), c_int32, c_float, c_float,
                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "lsx_gaussian_head_forward": (c_int32, [c_int32, POINTER(c_float), POINTER(c_float)] + [c_void_p] * 9),
-    "lsx_gaussian_head_backward": (c_int32, [c_int32, POINTER(c_float), POINTER(c_float)] + [c_void_p] * 14),
+    "lsx_gaussian_head_forward": (c_int32, [c_int32] + [c_void_p] * 11),
+    "lsx_gaussian_head_backward": (c_int32, [c_int32] + [c_void_p] * 16),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

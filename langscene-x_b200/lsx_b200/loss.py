@@ -51,13 +51,14 @@ class _ImageLoss(torch.autograd.Function):
     def backward(ctx, g_ssim, g_l1):
         img1, img2, dmaps = ctx.saved_tensors
         C, H, W = img1.shape
-        n = float(C * H * W)
-        k_ssim = 0.0 if g_ssim is None else float(g_ssim) / n     # one host read of two scalars per backward
-        k_l1 = 0.0 if g_l1 is None else float(g_l1) / n
+        dev = img1.device
+        scal = lambda t: None if t is None else t.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        gs, gl = scal(g_ssim), scal(g_l1)                          # device scalars: no host read in backward
         g = torch.empty_like(img1)
-        with torch.cuda.device(img1.device):
+        with torch.cuda.device(dev):
             _lib.check(_lib.load().lsx_image_loss_backward(C, H, W, img1.data_ptr(), img2.data_ptr(), dmaps.data_ptr(),
-                                                           k_ssim, k_l1, g.data_ptr(), _stream(img1.device)),
+                                                           None if gs is None else gs.data_ptr(),
+                                                           None if gl is None else gl.data_ptr(), g.data_ptr(), _stream(dev)),
                        "image_loss backward")
         return g, None
 

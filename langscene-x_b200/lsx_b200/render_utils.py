@@ -78,14 +78,14 @@ class _GaussianHead(torch.autograd.Function):
         if xyz.shape != (P, 3) or scaling_raw.shape != (P, 3) or rotation_raw.shape != (P, 4) or opacity_raw.numel() != P:
             raise RuntimeError("expected xyz (P,3), scaling (P,3), rotation (P,4), opacity (P,1)")
         xyz, scaling_raw, rotation_raw, opacity_raw = (t.contiguous() for t in (xyz, scaling_raw, rotation_raw, opacity_raw))
-        view = (ctypes.c_float * 16)(*viewmatrix.detach().reshape(-1).tolist())   # 19 floats host side: tiny D2H if on GPU
-        cam = (ctypes.c_float * 3)(*campos.detach().reshape(-1).tolist())
         dev = xyz.device
+        view = viewmatrix.detach().to(device=dev, dtype=torch.float32).contiguous()   # stays on the device: no host sync
+        cam = campos.detach().to(device=dev, dtype=torch.float32).contiguous()
         opts = dict(dtype=torch.float32, device=dev)
         scales, rotations = torch.empty((P, 3), **opts), torch.empty((P, 4), **opts)
         opacity, all_map = torch.empty((P, 1), **opts), torch.empty((P, 5), **opts)
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().lsx_gaussian_head_forward(P, view, cam, xyz.data_ptr(), scaling_raw.data_ptr(),
+            _lib.check(_lib.load().lsx_gaussian_head_forward(P, view.data_ptr(), cam.data_ptr(), xyz.data_ptr(), scaling_raw.data_ptr(),
                                                              rotation_raw.data_ptr(), opacity_raw.data_ptr(), scales.data_ptr(),
                                                              rotations.data_ptr(), opacity.data_ptr(), all_map.data_ptr(),
                                                              _stream(dev)), "gaussian_head")
@@ -105,7 +105,7 @@ class _GaussianHead(torch.autograd.Function):
         g_xyz, g_s, g_r = torch.empty((P, 3), **opts), torch.empty((P, 3), **opts), torch.empty((P, 4), **opts)
         g_o = torch.empty(opacity_raw.shape, **opts)
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().lsx_gaussian_head_backward(P, view, cam, xyz.data_ptr(), scaling_raw.data_ptr(),
+            _lib.check(_lib.load().lsx_gaussian_head_backward(P, view.data_ptr(), cam.data_ptr(), xyz.data_ptr(), scaling_raw.data_ptr(),
                                                               rotation_raw.data_ptr(), opacity_raw.data_ptr(), dp(g_scales),
                                                               dp(g_rotations), dp(g_opacity), dp(g_all_map), None,
                                                               g_xyz.data_ptr(), g_s.data_ptr(), g_r.data_ptr(), g_o.data_ptr(),
