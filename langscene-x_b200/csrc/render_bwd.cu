@@ -11,9 +11,10 @@
 //
 // B200 design
 //   * the per-channel "accumulated colour behind" recurrence is linear, so its dot product with the
-//     pixel's upstream gradient is carried as ONE scalar:  A <- a_prev * s_prev + (1 - a_prev) * A  with
-//     s = <feat[g], dL/dpix>.  That removes 2*Ct registers and ~3*Ct flops per blend compared with the
-//     per-channel form.
+//     pixel's upstream gradient is carried as ONE scalar:  B <- alpha * s + (1 - alpha) * B  with
+//     s = <feat[g], dL/dpix>, and dL/dalpha = (s - B_behind) * T.  That removes 2*Ct registers and ~3*Ct flops
+//     per blend compared with the per-channel form.  (Its rounding differs from the reference's per-channel
+//     differences by O(1e-7 |s| / |s - B|); see the tolerance note in tests/test_parity_gpu.py.)
 //   * ONE WARP PER CTA: warp = one 8x4 pixel block of a tile; it stages (TMA, double-buffered, tile_stage.cuh)
 //     and visits only the list entries whose footprint-mask bit for its block is set (cull.cu), back to front,
 //     starting below the block's deepest contributor.  No CTA-wide barrier anywhere.
@@ -23,7 +24,10 @@
 //     Per entry the 32 weights alpha*T are exchanged through 128 B of shared memory and lane c evaluates
 //     its channel's sum with 8 broadcast LDS.128 + 32 FFMA — no shuffles, no selects — then issues ONE
 //     RED.ADD.F32 into the packed per-Gaussian gradient record (the Ct lanes hit consecutive addresses).
-//     Only the 8 geometry terms (mean2D, |mean2D|, conic, opacity) go through a transposing butterfly.
+//     The 8 geometry terms (mean2D, |mean2D|, conic, opacity) go through a transposing shuffle butterfly that
+//     is issued one entry late (its 5 dependent levels overlap the next entry's load -> exp chain) — or, when
+//     at most 24 channels are blended (the reference's own 3-d feature configuration), through the same
+//     outer-product phase: the idle lanes 24..31 sum one geometry term each, no butterfly at all.
 //     The reference issues Ct + 8 global atomics per (pixel, Gaussian); this kernel issues Ct + 8 per
 //     (32-pixel block, Gaussian), all into one contiguous 144-B record.
 //   * warp-ballot skip of entries no lane blends.
