@@ -43,7 +43,7 @@ extern "C" {
 #define LSX_API
 #endif
 
-#define LSX_ABI_VERSION 2
+#define LSX_ABI_VERSION 3
 #define LSX_MAX_BLEND_CHANNELS 40 /* 3 + F + Fi + 5 must not exceed this */
 
 /* scratch allocation callback: must return a device pointer to at least `bytes` bytes, aligned to
@@ -219,6 +219,91 @@ LSX_API int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const
 LSX_API int lsx_arena_adam_step(int64_t n, int32_t n_groups, const int64_t* group_begin_host, const float* group_lr_host,
                                 int32_t step, float beta1, float beta2, float eps, float* params, const float* grads,
                                 float* exp_avg, float* exp_avg_sq, void* stream);
+
+/* ---- next row: densification / pruning on the flat arenas -------------------------------------------------
+ * Replaces GaussianModel.add_densification_stats / densify_and_prune / reset_opacity and the optimizer-state surgery under them
+ * (field_construction/scene/gaussian_model.py:443-446,506-724; call sites field_construction/gaussian_field.py:519-535).
+ *
+ * lsx_densify_stats_update: one view's statistics.  For rows with radii > 0: grad_accum += |dL_dmeans2D.xy|, grad_accum_abs +=
+ *   |dL_dmeans2D_abs.xy|, denom += 1 (the reference's denom_abs always equals denom); max_radii2D = max(max_radii2D, radii)
+ *   where additionally out_observe > 0 (NULL = no such filter).  dL_dmeans2D* are the (P,3) tensors the rasterizer returns. */
+LSX_API int lsx_densify_stats_update(int32_t P, const float* dL_dmeans2D, const float* dL_dmeans2D_abs, const int32_t* radii,
+                                     const int32_t* out_observe, float* grad_accum, float* grad_accum_abs, float* denom,
+                                     float* max_radii2D, void* stream);
+
+/* lsx_densify_plan: decides, for the P current rows, which are cloned, split (N = 2) and pruned, exactly as
+ * densify_and_prune(max_grad, abs_max_grad, min_opacity, extent, max_screen_size) does, and lays out the rows of the new set:
+ *   [surviving originals | surviving clones | surviving first children | surviving second children]  (the reference's order).
+ * Device scratch: `workspace` of lsx_densify_workspace_bytes(P) bytes, which also holds the two result arrays
+ *   row_map[P_new]     = kind << 30 | source row   (kind 0 original, 1 clone, 2 / 3 first / second split child)
+ *   noise_index[P_new] = row of z_clone (kind 1) / z_split (kind 2, 3) the reference's sampling order assigns, -1 for kind 0
+ * valid until the workspace is released.  Synchronises the stream (the host needs the counts: 2 reads, +1 per capped branch).
+ * Thresholds must be > 0.  prune_world_size = bool(max_screen_size): the reference zeroes max_radii2D before its final prune,
+ * so the screen-size value itself never matters and only the world-size test (> 0.1 * extent) is switched — reproduced. */
+typedef struct lsx_densify_plan_args {
+    int32_t P;
+    const float* grad_accum;      /* (P) */
+    const float* grad_accum_abs;  /* (P) */
+    const float* denom;           /* (P) */
+    const float* max_radii2D;     /* (P) */
+    const float* scaling_raw;     /* (P,3) log scales  */
+    const float* opacity_raw;     /* (P)   logit opacity */
+    float max_grad, abs_max_grad, min_opacity, extent;
+    float percent_dense, abs_split_radii2D_threshold;
+    int64_t max_all_points, max_abs_split_points;
+    int32_t prune_world_size;
+    void* workspace;
+    size_t workspace_bytes;
+    void* stream;
+} lsx_densify_plan_args;
+
+typedef struct lsx_densify_plan_result {
+    int64_t P_new;
+    int64_t n_clone, n_split;  /* selected (pre-prune): z_clone needs n_clone rows, z_split 2 * n_split rows */
+    int64_t n_split_abs;       /* of n_split, selected by the abs-gradient pass */
+    int64_t n_kept_original, n_kept_clone, n_kept_split;
+    int32_t clone_capped, split_capped, abs_capped;  /* which max_all_points / max_abs_split_points branches were taken */
+    const uint32_t* row_map;      /* device, inside the workspace */
+    const int32_t* noise_index;   /* device, inside the workspace */
+} lsx_densify_plan_result;
+
+LSX_API size_t lsx_densify_workspace_bytes(int32_t P);
+LSX_API int lsx_densify_plan(const lsx_densify_plan_args* args, lsx_densify_plan_result* out);
+
+/* lsx_densify_apply: builds the new arenas with ONE gather per group: new[new_begin[k] + dst * width[k] + c] =
+ * old[old_begin[k] + src * width[k] + c]; exp_avg / exp_avg_sq likewise for surviving originals and zero for new rows (all four
+ * moment pointers may be NULL).  Roles: new rows of the XYZ group get xyz + R(q/|q|) (exp(s) * z) (z = unit normal noise,
+ * (n_clone,3) and (2 n_split,3) as the reference draws it: first children, then second children), split children of the SCALING
+ * group get log(exp(s) / 1.6); ROTATION marks the quaternion group.  old_begin / new_begin / width / role are HOST arrays. */
+enum lsx_densify_role { LSX_DENSIFY_ROLE_COPY = 0, LSX_DENSIFY_ROLE_XYZ = 1, LSX_DENSIFY_ROLE_SCALING = 2,
+                        LSX_DENSIFY_ROLE_ROTATION = 3 };
+typedef struct lsx_densify_apply_args {
+    int64_t P_new;
+    int64_t n_new_rows;           /* P_new - n_kept_original */
+    int32_t n_groups;             /* <= LSX_ADAM_MAX_GROUPS */
+    const int64_t* old_begin;     /* element offsets of the groups inside the old / new arenas */
+    const int64_t* new_begin;
+    const int32_t* width;         /* floats per row */
+    const int32_t* role;
+    const uint32_t* row_map;
+    const int32_t* noise_index;
+    const float* z_clone;
+    const float* z_split;
+    const float* old_params;
+    const float* old_exp_avg;
+    const float* old_exp_avg_sq;
+    float* new_params;
+    float* new_exp_avg;
+    float* new_exp_avg_sq;
+    void* stream;
+    int32_t group_align;          /* > 1: every group of the NEW arenas is zero-filled up to the next multiple of this many
+                                   * elements past its last row (the arenas may then be allocated uninitialised) */
+} lsx_densify_apply_args;
+LSX_API int lsx_densify_apply(const lsx_densify_apply_args* args);
+
+/* opacity_raw = inverse_sigmoid(min(sigmoid(opacity_raw), 0.01)), moments of that group zeroed (NULL = absent)
+ * (GaussianModel.reset_opacity, gaussian_model.py:443-446 + replace_tensor_to_optimizer :506-518). */
+LSX_API int lsx_reset_opacity(int32_t P, float* opacity_raw, float* exp_avg, float* exp_avg_sq, void* stream);
 
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("LSX_B200_LIB", os.path.join(_PKG_DIR, "liblsx_b200.so
 
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_BLEND_CHANNELS = 40
 
 
@@ -68,6 +68,40 @@ class ScratchLayout(ctypes.Structure):
     ]
 
 
+class DensifyPlanArgs(ctypes.Structure):
+    _fields_ = [
+        ("P", c_int32), ("grad_accum", c_void_p), ("grad_accum_abs", c_void_p), ("denom", c_void_p), ("max_radii2D", c_void_p),
+        ("scaling_raw", c_void_p), ("opacity_raw", c_void_p),
+        ("max_grad", c_float), ("abs_max_grad", c_float), ("min_opacity", c_float), ("extent", c_float),
+        ("percent_dense", c_float), ("abs_split_radii2D_threshold", c_float),
+        ("max_all_points", ctypes.c_int64), ("max_abs_split_points", ctypes.c_int64),
+        ("prune_world_size", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t), ("stream", c_void_p),
+    ]
+
+
+class DensifyPlanResult(ctypes.Structure):
+    _fields_ = [
+        ("P_new", ctypes.c_int64), ("n_clone", ctypes.c_int64), ("n_split", ctypes.c_int64), ("n_split_abs", ctypes.c_int64),
+        ("n_kept_original", ctypes.c_int64), ("n_kept_clone", ctypes.c_int64), ("n_kept_split", ctypes.c_int64),
+        ("clone_capped", c_int32), ("split_capped", c_int32), ("abs_capped", c_int32),
+        ("row_map", c_void_p), ("noise_index", c_void_p),
+    ]
+
+
+class DensifyApplyArgs(ctypes.Structure):
+    _fields_ = [
+        ("P_new", ctypes.c_int64), ("n_new_rows", ctypes.c_int64), ("n_groups", c_int32),
+        ("old_begin", POINTER(ctypes.c_int64)), ("new_begin", POINTER(ctypes.c_int64)),
+        ("width", POINTER(c_int32)), ("role", POINTER(c_int32)),
+        ("row_map", c_void_p), ("noise_index", c_void_p), ("z_clone", c_void_p), ("z_split", c_void_p),
+        ("old_params", c_void_p), ("old_exp_avg", c_void_p), ("old_exp_avg_sq", c_void_p),
+        ("new_params", c_void_p), ("new_exp_avg", c_void_p), ("new_exp_avg_sq", c_void_p),
+        ("stream", c_void_p), ("group_align", c_int32),
+    ]
+
+
+DENSIFY_ROLE = {"copy": 0, "xyz": 1, "scaling": 2, "rotation": 3}
+
 # every symbol include/lsx_rasterizer.h declares: name -> (restype, argtypes)
 EXPORTS = {
     "lsx_rasterize_forward": (c_int32, [POINTER(ForwardArgs), POINTER(c_int32)]),
@@ -86,6 +120,11 @@ EXPORTS = {
                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_gaussian_head_forward": (c_int32, [c_int32] + [c_void_p] * 11),
     "lsx_gaussian_head_backward": (c_int32, [c_int32] + [c_void_p] * 16),
+    "lsx_densify_stats_update": (c_int32, [c_int32] + [c_void_p] * 9),
+    "lsx_densify_workspace_bytes": (c_size_t, [c_int32]),
+    "lsx_densify_plan": (c_int32, [POINTER(DensifyPlanArgs), POINTER(DensifyPlanResult)]),
+    "lsx_densify_apply": (c_int32, [POINTER(DensifyApplyArgs)]),
+    "lsx_reset_opacity": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

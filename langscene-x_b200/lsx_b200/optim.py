@@ -10,22 +10,31 @@ import ctypes
 import torch
 
 from . import _lib
-from .multiview import PARAM_GROUPS, GradArena
+from .multiview import GradArena
 
 
 class ArenaAdam:
     def __init__(self, params: GradArena, lrs, betas=(0.9, 0.999), eps=1e-15):
         if not params.flat.is_cuda:
             raise RuntimeError("ArenaAdam needs CUDA arenas (this operator has no CPU path)")
-        self.params = params
-        self.exp_avg = torch.zeros_like(params.flat)
-        self.exp_avg_sq = torch.zeros_like(params.flat)
         self.betas, self.eps, self.step_count = betas, eps, 0
         self.lrs = dict(lrs)
-        names = [n for n in PARAM_GROUPS if params.offsets[n][1] > 0]
+        self.rebind(params, torch.zeros_like(params.flat), torch.zeros_like(params.flat))
+
+    def rebind(self, params: GradArena, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor):
+        """Point the optimiser at new arenas (after lsx_b200.densify.densify_and_prune: pass result.params and the `.flat`
+        tensors of result.exp_avg / result.exp_avg_sq).  The step count is kept, as torch.optim.Adam keeps its per-parameter
+        `step` through the reference's cat / prune surgery (gaussian_model.py:520-581)."""
+        if exp_avg.numel() != params.flat.numel() or exp_avg_sq.numel() != params.flat.numel():
+            raise RuntimeError("moment arenas and parameter arena have different layouts")
+        self.params, self.exp_avg, self.exp_avg_sq = params, exp_avg, exp_avg_sq
+        # groups in arena order (dicts keep insertion order): lsx_b200.multiview.PARAM_GROUPS for a GradArena-shaped arena,
+        # the reference's own optimizer groups for a lsx_b200.densify.ParamArena
+        names = [n for n in params.offsets if params.offsets[n][1] > 0]
         self._names = names
         begins = [params.offsets[n][0] for n in names] + [params.flat.numel()]
         self._begin = (ctypes.c_int64 * len(begins))(*begins)
+        return self
 
     def set_lr(self, name, lr):
         """e.g. the exponential xyz schedule of GaussianModel.update_learning_rate"""

@@ -32,7 +32,8 @@ def test_ctypes_structs_match_c_layout():
     """Compile a tiny C program against the header and compare sizeof / offsetof with ctypes."""
     from lsx_b200 import _lib
     structs = {"lsx_forward_args": _lib.ForwardArgs, "lsx_backward_args": _lib.BackwardArgs,
-               "lsx_scratch_layout": _lib.ScratchLayout}
+               "lsx_scratch_layout": _lib.ScratchLayout, "lsx_densify_plan_args": _lib.DensifyPlanArgs,
+               "lsx_densify_plan_result": _lib.DensifyPlanResult, "lsx_densify_apply_args": _lib.DensifyApplyArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
