@@ -305,6 +305,32 @@ LSX_API int lsx_densify_apply(const lsx_densify_apply_args* args);
  * (GaussianModel.reset_opacity, gaussian_model.py:443-446 + replace_tensor_to_optimizer :506-518). */
 LSX_API int lsx_reset_opacity(int32_t P, float* opacity_raw, float* exp_avg, float* exp_avg_sq, void* stream);
 
+/* ---- next row (pose half of the render wrapper) -------------------------------------------------------------
+ * render(..., camera_pose=pose) of field_construction/gaussian_renderer/__init__.py:79-87 with pose = [quaternion(4) | T(3)]
+ * (a DEVICE array of 7 floats, one row of GaussianModel.P):
+ *   out_means3D   = R(q/|q|) xyz + T              (get_camera_from_tensor / quad2rotation, field_construction/utils/pose_utils.py:13-87)
+ *   out_rotations = q (x) rotation_raw            (quadmultiply, pose_utils.py:89-107: Hamilton product with the RAW pose quaternion)
+ * rotation_raw / out_rotations may both be NULL.  backward: dL_dxyz (P,3), dL_drotation_raw (P,4, may be NULL) and dL_dpose (7)
+ * from the gradients the rasterizer returns for means3D / rotations (either may be NULL = zero); `partials` is device scratch of
+ * lsx_pose_num_partials() floats.  The pose gradient is reduced in a fixed order (deterministic, no atomics). */
+LSX_API int32_t lsx_pose_num_partials(void);
+LSX_API int lsx_pose_transform_forward(int32_t P, const float* pose, const float* xyz, const float* rotation_raw,
+                                       float* out_means3D, float* out_rotations, void* stream);
+LSX_API int lsx_pose_transform_backward(int32_t P, const float* pose, const float* xyz, const float* rotation_raw,
+                                        const float* dL_dmeans3D, const float* dL_drotations, float* dL_dxyz,
+                                        float* dL_drotation_raw, float* dL_dpose, float* partials, void* stream);
+
+/* ---- next row: masked L1 of the language-feature loss ------------------------------------------------------
+ * l1_loss(a * mask, b * mask) = mean |a*mask - b*mask| over C*H*W (field_construction/gaussian_field.py:450-451,
+ * field_construction/utils/loss_utils.py:20-21); a, b planar C*H*W, mask H*W (mask_channels 1, broadcast) or C*H*W, NULL = ones.
+ * forward : partial[0 .. lsx_masked_l1_num_blocks(C*H*W)) = per-block sums; the caller adds them and divides by C*H*W.
+ * backward: dL_da = *upstream / (C*H*W) * sign(a*mask - b*mask) * mask, fully written; upstream is a DEVICE scalar (NULL = 1). */
+LSX_API int32_t lsx_masked_l1_num_blocks(int64_t n);
+LSX_API int lsx_masked_l1_forward(int32_t C, int32_t H, int32_t W, int32_t mask_channels, const float* a, const float* b,
+                                  const float* mask, float* partial, void* stream);
+LSX_API int lsx_masked_l1_backward(int32_t C, int32_t H, int32_t W, int32_t mask_channels, const float* a, const float* b,
+                                   const float* mask, const float* upstream, float* dL_da, void* stream);
+
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 
 /* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the

@@ -125,6 +125,12 @@ EXPORTS = {
     "lsx_densify_plan": (c_int32, [POINTER(DensifyPlanArgs), POINTER(DensifyPlanResult)]),
     "lsx_densify_apply": (c_int32, [POINTER(DensifyApplyArgs)]),
     "lsx_reset_opacity": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsx_pose_num_partials": (c_int32, []),
+    "lsx_pose_transform_forward": (c_int32, [c_int32] + [c_void_p] * 6),
+    "lsx_pose_transform_backward": (c_int32, [c_int32] + [c_void_p] * 10),
+    "lsx_masked_l1_num_blocks": (c_int32, [ctypes.c_int64]),
+    "lsx_masked_l1_forward": (c_int32, [c_int32, c_int32, c_int32, c_int32] + [c_void_p] * 5),
+    "lsx_masked_l1_backward": (c_int32, [c_int32, c_int32, c_int32, c_int32] + [c_void_p] * 6),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),

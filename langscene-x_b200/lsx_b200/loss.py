@@ -72,3 +72,53 @@ def ssim(img1, img2, window_size=11, size_average=True):
 def image_loss(image, gt, lambda_dssim):
     s, l1 = _ImageLoss.apply(image, gt)
     return (1.0 - lambda_dssim) * l1 + lambda_dssim * (1.0 - s), l1, s
+
+
+class _MaskedL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, mask):
+        _check_pair(a, b)
+        if b.requires_grad:
+            raise RuntimeError("the second tensor is treated as ground truth: it must not require grad")
+        ac, bc = a.contiguous(), b.contiguous()
+        C, H, W = ac.shape
+        mc = 1
+        if mask is not None:
+            mask = mask.detach().to(device=a.device, dtype=torch.float32)
+            if mask.numel() == H * W:
+                mask = mask.reshape(H, W).contiguous()
+            elif tuple(mask.shape) == (C, H, W):
+                mask, mc = mask.contiguous(), C
+            else:
+                raise RuntimeError("mask must have H*W elements (broadcast over channels) or shape (C, H, W)")
+        lib = _lib.load()
+        nblk = int(lib.lsx_masked_l1_num_blocks(C * H * W))
+        partial = torch.empty(nblk, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib.check(lib.lsx_masked_l1_forward(C, H, W, mc, ac.data_ptr(), bc.data_ptr(),
+                                                 None if mask is None else mask.data_ptr(), partial.data_ptr(),
+                                                 _stream(a.device)), "masked_l1")
+        ctx.save_for_backward(ac, bc, mask if mask is not None else torch.empty(0, device=a.device))
+        ctx.mc = mc
+        return partial.sum() / float(C * H * W)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, mask = ctx.saved_tensors
+        C, H, W = a.shape
+        dev = a.device
+        up = g.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()     # device scalar: no host read
+        out = torch.empty_like(a)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().lsx_masked_l1_backward(C, H, W, ctx.mc, a.data_ptr(), b.data_ptr(),
+                                                          mask.data_ptr() if mask.numel() else None, up.data_ptr(),
+                                                          out.data_ptr(), _stream(dev)), "masked_l1 backward")
+        return out, None, None
+
+
+def masked_l1_loss(network_output, gt, mask=None):
+    """l1_loss(network_output * mask, gt * mask) of the language-feature supervision (field_construction/gaussian_field.py:
+    450-451; l1_loss = mean |a - b|, field_construction/utils/loss_utils.py:20-21) in one kernel each way.  `mask`: (H, W) /
+    (1, H, W) bool or float (as Camera.get_language_feature returns it, field_construction/scene/cameras.py:137-151), or
+    (C, H, W); None = plain l1_loss.  Gradient flows to `network_output` only."""
+    return _MaskedL1.apply(network_output, gt, mask)

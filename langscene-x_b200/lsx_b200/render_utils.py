@@ -120,3 +120,60 @@ def gaussian_head(xyz, scaling_raw, rotation_raw, opacity_raw, viewmatrix, campo
     The position gradient returned for `xyz` is only the part that flows through all_map; the rasterizer's own
     dL/dmeans3D reaches `xyz` through autograd as usual."""
     return _GaussianHead.apply(xyz, scaling_raw, rotation_raw, opacity_raw, viewmatrix, campos)
+
+
+class _PoseTransform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, xyz, rotation_raw):
+        for name, t in (("pose", pose), ("xyz", xyz), ("rotation", rotation_raw)):
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise RuntimeError(f"{name} must be a CUDA tensor (this operator has no CPU path)")
+            if t.dtype != torch.float32:
+                raise RuntimeError(f"{name} must be float32")
+        P = int(xyz.shape[0])
+        if pose.numel() != 7 or xyz.shape != (P, 3) or (rotation_raw is not None and rotation_raw.shape != (P, 4)):
+            raise RuntimeError("expected pose (7,) = [quaternion | translation], xyz (P,3), rotation (P,4)")
+        pose, xyz = pose.reshape(7).contiguous(), xyz.contiguous()
+        rot = None if rotation_raw is None else rotation_raw.contiguous()
+        dev = xyz.device
+        out_xyz = torch.empty_like(xyz)
+        out_rot = None if rot is None else torch.empty_like(rot)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().lsx_pose_transform_forward(P, pose.data_ptr(), xyz.data_ptr(), None if rot is None else rot.data_ptr(),
+                                                              out_xyz.data_ptr(), None if rot is None else out_rot.data_ptr(),
+                                                              _stream(dev)), "pose_transform")
+        ctx.save_for_backward(pose, xyz, rot if rot is not None else torch.empty(0, device=dev))
+        ctx.pose_shape = pose.shape
+        if rot is None:
+            return out_xyz, torch.empty(0, device=dev)
+        return out_xyz, out_rot
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_rot):
+        pose, xyz, rot = ctx.saved_tensors
+        P, dev = int(xyz.shape[0]), xyz.device
+        has_rot = rot.numel() > 0
+        c = lambda t: None if t is None else t.to(torch.float32).contiguous()
+        g_xyz, g_rot = c(g_xyz), (c(g_rot) if has_rot else None)
+        lib = _lib.load()
+        d_xyz = torch.empty_like(xyz)
+        d_rot = torch.empty_like(rot) if has_rot else None
+        d_pose = torch.empty(7, dtype=torch.float32, device=dev)
+        partials = torch.empty(int(lib.lsx_pose_num_partials()), dtype=torch.float32, device=dev)
+        dp = lambda t: None if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(lib.lsx_pose_transform_backward(P, pose.data_ptr(), xyz.data_ptr(), dp(rot) if has_rot else None, dp(g_xyz),
+                                                       dp(g_rot), d_xyz.data_ptr(), dp(d_rot), d_pose.data_ptr(),
+                                                       partials.data_ptr(), _stream(dev)), "pose_transform backward")
+        return d_pose, d_xyz, d_rot
+
+
+def pose_transform(camera_pose, xyz, rotation_raw=None):
+    """(means3D, rotations) of render(..., camera_pose=pose) (field_construction/gaussian_renderer/__init__.py:79-87):
+    means3D = (get_camera_from_tensor(pose) @ [xyz 1]^T)^T[:, :3], rotations = quadmultiply(pose[:4], rotation_raw)
+    (field_construction/utils/pose_utils.py:13-107).  camera_pose: (7,) = [quaternion (w,x,y,z) | translation], a row of
+    GaussianModel.P; gradients flow to the pose (reduced over all Gaussians inside the backward kernel), xyz and rotation."""
+    out_xyz, out_rot = _PoseTransform.apply(camera_pose, xyz, rotation_raw)
+    return (out_xyz, out_rot) if rotation_raw is not None else (out_xyz, None)
