@@ -331,6 +331,16 @@ LSX_API int lsx_masked_l1_forward(int32_t C, int32_t H, int32_t W, int32_t mask_
 LSX_API int lsx_masked_l1_backward(int32_t C, int32_t H, int32_t W, int32_t mask_channels, const float* a, const float* b,
                                    const float* mask, const float* upstream, float* dL_da, void* stream);
 
+/* ---- next row: row pack / unpack for the on-disk formats ----------------------------------------------------
+ * GaussianModel.save_ply / load_ply (field_construction/scene/gaussian_model.py:415-441,448-504) convert between the per-group
+ * parameter tensors and one row of ncols floats per Gaussian.  rows[r * ncols + c] = arena[col_begin[c] + r * col_stride[c]]
+ * (col_begin[c] < 0: the column is constant 0 on pack and ignored on unpack — the PLY's unused normals).  col_begin / col_stride
+ * are DEVICE arrays of ncols entries; rows is a device buffer of P * ncols floats (the PLY body, ready for one D2H copy). */
+LSX_API int lsx_rows_pack(int64_t P, int32_t ncols, const int64_t* col_begin, const int32_t* col_stride, const float* arena,
+                          float* rows, void* stream);
+LSX_API int lsx_rows_unpack(int64_t P, int32_t ncols, const int64_t* col_begin, const int32_t* col_stride, const float* rows,
+                            float* arena, void* stream);
+
 /* ---- parity / introspection helpers (used by the tests; not on the hot path) ------------------- */
 
 /* Offsets (bytes from the buffer base) of the private scratch arrays, so tests can read the

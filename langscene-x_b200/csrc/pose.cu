@@ -262,3 +262,64 @@ extern "C" int lsx_masked_l1_backward(int32_t C, int32_t H, int32_t W, int32_t m
     LSX_KERNEL_OK(stream, false);
     return 0;
 }
+
+// ---- row pack / unpack for the on-disk formats ------------------------------------------------
+// GaussianModel.save_ply / load_ply (field_construction/scene/gaussian_model.py:415-441,448-504) move between the optimiser's
+// per-group tensors and ONE row of `ncols` floats per Gaussian (x y z nx ny nz f_dc_* f_rest_* opacity scale_* rot_*
+// language_feature_* instance_feature_*; SH coefficients transposed to channel-major).  The reference does it on the host
+// (numpy concatenate + a Python tuple per row); here it is one gather / scatter over the arena on the device:
+//     rows[r * ncols + c] = arena[col_begin[c] + r * col_stride[c]]      (col_begin[c] < 0: constant 0, the normals)
+namespace lsx {
+namespace {
+__global__ void __launch_bounds__(256) rows_pack_kernel(const long long n, const int ncols, const long long* __restrict__ col_begin,
+                                                        const int* __restrict__ col_stride, const float* __restrict__ arena,
+                                                        float* __restrict__ rows) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / ncols;
+        const int c = (int)(e - r * ncols);
+        const long long b = col_begin[c];
+        rows[e] = b < 0 ? 0.f : arena[b + r * col_stride[c]];
+    }
+}
+__global__ void __launch_bounds__(256) rows_unpack_kernel(const long long n, const int ncols, const long long* __restrict__ col_begin,
+                                                          const int* __restrict__ col_stride, const float* __restrict__ rows,
+                                                          float* __restrict__ arena) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / ncols;
+        const int c = (int)(e - r * ncols);
+        const long long b = col_begin[c];
+        if (b >= 0) arena[b + r * col_stride[c]] = rows[e];
+    }
+}
+}  // namespace
+}  // namespace lsx
+
+extern "C" int lsx_rows_pack(int64_t P, int32_t ncols, const int64_t* col_begin, const int32_t* col_stride, const float* arena,
+                             float* rows, void* stream_) {
+    if (P < 0 || ncols <= 0 || !col_begin || !col_stride || (P > 0 && (!arena || !rows))) {
+        set_error("lsx_rows_pack: bad arguments");
+        return -1;
+    }
+    if (P == 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long n = P * ncols, want = (n + 255) / 256;
+    rows_pack_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, stream>>>(n, ncols, (const long long*)col_begin, col_stride,
+                                                                                arena, rows);
+    LSX_KERNEL_OK(stream, false);
+    return 0;
+}
+
+extern "C" int lsx_rows_unpack(int64_t P, int32_t ncols, const int64_t* col_begin, const int32_t* col_stride, const float* rows,
+                               float* arena, void* stream_) {
+    if (P < 0 || ncols <= 0 || !col_begin || !col_stride || (P > 0 && (!arena || !rows))) {
+        set_error("lsx_rows_unpack: bad arguments");
+        return -1;
+    }
+    if (P == 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long n = P * ncols, want = (n + 255) / 256;
+    rows_unpack_kernel<<<(int)(want < 148 * 32 ? want : 148 * 32), 256, 0, stream>>>(n, ncols, (const long long*)col_begin,
+                                                                                  col_stride, rows, arena);
+    LSX_KERNEL_OK(stream, false);
+    return 0;
+}
