@@ -24,10 +24,10 @@
 //     Per entry the 32 weights alpha*T are exchanged through 128 B of shared memory and lane c evaluates
 //     its channel's sum with 8 broadcast LDS.128 + 32 FFMA — no shuffles, no selects — then issues ONE
 //     RED.ADD.F32 into the packed per-Gaussian gradient record (the Ct lanes hit consecutive addresses).
-//     The 8 geometry terms (mean2D, |mean2D|, conic, opacity) go through a transposing shuffle butterfly that
-//     is issued one entry late (its 5 dependent levels overlap the next entry's load -> exp chain) — or, when
-//     at most 24 channels are blended (the reference's own 3-d feature configuration), through the same
-//     outer-product phase: the idle lanes 24..31 sum one geometry term each, no butterfly at all.
+//     The 8 geometry terms (mean2D, |mean2D|, conic, opacity) are exchanged through shared memory the same way: when
+//     at most 24 channels are blended (the reference's own 3-d feature configuration) the idle lanes 24..31 sum one
+//     term each inside the outer-product phase; otherwise every lane sums 8 pixels of one term (2 LDS.128 + 7 FADD)
+//     and two shuffles, issued one entry late so that they overlap the next entry's load -> exp chain, finish it.
 //     The reference issues Ct + 8 global atomics per (pixel, Gaussian); this kernel issues Ct + 8 per
 //     (32-pixel block, Gaussian), all into one contiguous 144-B record.
 //   * warp-ballot skip of entries no lane blends.
@@ -39,27 +39,6 @@ namespace lsx {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
-
-// Transposing butterfly: on entry every lane holds N partial values v[0..N); on exit v[0] of lane L holds the
-// warp-wide sum of value (L >> (5 - log2 N)).  N-1 + (5 - log2 N) shuffles in total.
-template <int N, int OFF>
-struct WarpTransposeReduce {
-    static __device__ __forceinline__ void run(float* v, const unsigned lane) {
-        if constexpr (N > 1) {
-            const bool upper = (lane & OFF) != 0;
-#pragma unroll
-            for (int i = 0; i < N / 2; ++i) {
-                const float send = upper ? v[i] : v[i + N / 2];
-                const float keep = upper ? v[i + N / 2] : v[i];
-                v[i] = keep + __shfl_xor_sync(kFull, send, OFF);
-            }
-            if constexpr (OFF > 1) WarpTransposeReduce<N / 2, OFF / 2>::run(v, lane);
-        } else {
-            v[0] += __shfl_xor_sync(kFull, v[0], OFF);
-            if constexpr (OFF > 1) WarpTransposeReduce<1, OFF / 2>::run(v, lane);
-        }
-    }
-};
 
 // Upstream gradient of every blended channel at one pixel (planar inputs), with the plane-depth gradient folded
 // into the map channels (backward.cu:479-503); bg_dot = <background, dL/dcolor>.
@@ -113,25 +92,28 @@ __device__ __forceinline__ void load_pixel_gradients(const RenderParams& p, cons
 
 }
 
-template <int CT4, int CHUNK>
-__global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
+template <int CT4, int CHUNK, int MB>
+__global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     constexpr int GS = CT4 + 8;                // floats per packed gradient record
     constexpr int NPASS = (CT4 + 31) / 32;     // channel passes of the outer-product accumulation
     constexpr int TS = CT4 + 1;                // row stride of the one-time transposition scratch (odd -> conflict-free)
-    // Lanes CT4..31 have no channel to sum in the outer-product phase: they sum geometry terms instead (the term's
-    // 32 per-pixel values are exchanged like the weights, the lane's "gradient view" is all ones).  NGL terms go
-    // that way, the remaining NB = 8 - NGL through the shuffle butterfly.  Only the all-or-nothing split is used:
-    // with 27 channels (4 free lanes) the mixed variant costs 27 more registers than it saves in instructions
-    // (measured: 2.56 -> 2.66 ms at C3), with <= 24 channels all 8 terms fit (C4: 0.51 -> 0.44 ms).
+    // The 8 geometry terms (mean2D.xy, |mean2D|.xy, conic xyw, opacity) of an entry are exchanged through shared memory
+    // like the weights.  With <= 24 channels the idle lanes CT4..31 sum one term each in the outer-product phase itself
+    // (their "gradient view" is all ones; C4: 0.51 -> 0.44 ms).  Otherwise lane L sums term L >> 2 over pixels
+    // 8 (L & 3) .. + 7 with two LDS.128 + 7 FADD and two shuffles, issued one entry late, finish the sum: ~24
+    // instructions and one carried register instead of the ~43 and eight of a transposing shuffle butterfly
+    // (C3: 2.56 -> 2.47 ms together with 16-entry rounds, which give the 2.6 KB of exchange space back to occupancy).
+    // A mixed split (4 idle lanes at 27 channels + 4 terms elsewhere) costs more registers than it saves: 2.56 -> 2.66 ms.
     constexpr int NGL = (NPASS == 1 && 32 - CT4 >= 8) ? 8 : 0;
-    constexpr int NB = (8 - NGL) == 0 ? 0 : ((8 - NGL) <= 4 ? 4 : 8);   // butterfly width (power of two)
+    constexpr bool kGeoSmem = (NGL == 0);
+    constexpr int NX = 8;                      // geometry arrays exchanged through smem
     constexpr int XROW = 36;                   // floats between exchanged arrays: 16-B aligned, bank offset 4 per array
     using Stage = WarpStage<RS, CHUNK>;
     static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(16) float s_w[2][(1 + NGL) * XROW];  // weights + NGL geometry terms, double buffered
+    __shared__ __align__(16) float s_w[2][(1 + NX) * XROW];  // weights + NX geometry terms, double buffered
 
     const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -185,7 +167,7 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
     const float ddely_dy = 0.5f * (float)p.H;
     const uint32_t w_addr = smem_u32(&s_w[0][0]);
     unsigned parity = 0;
-    float pv[NB > 0 ? NB : 1];  // geometry terms of the last blended entry still to be reduced by the butterfly
+    float psum = 0.f;           // kGeoSmem: this lane's 8-pixel partial sum of term lane >> 2 of the last blended entry
     float* pgrec = nullptr;
     bool pend = false;    // warp-uniform
 
@@ -216,14 +198,13 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             ia += 4;
             const float4 h0 = lds128(ra);
             const float2 h1 = lds64(ra + 16);
-            // Geometry terms of the PREVIOUS blended entry: their shuffle butterfly (5 dependent levels) is issued
-            // here so that its latency overlaps this entry's load -> power -> exp -> alpha chain.
-            if constexpr (NB > 0) {
+            // Geometry terms of the PREVIOUS blended entry: the last two reduction levels are issued here so that
+            // their latency overlaps this entry's load -> power -> exp -> alpha chain.
+            if constexpr (kGeoSmem) {
                 if (pend) {
-                    WarpTransposeReduce<NB, 16>::run(pv, lane);
-                    constexpr int kShift = NB == 8 ? 2 : 3;  // value k ends in lanes k << kShift
-                    if ((lane & ((1u << kShift) - 1u)) == 0u && pv[0] != 0.f)
-                        atomicAdd(pgrec + CT4 + NGL + (lane >> kShift), pv[0]);
+                    psum += __shfl_xor_sync(kFull, psum, 1);
+                    psum += __shfl_xor_sync(kFull, psum, 2);
+                    if ((lane & 3u) == 0u && psum != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), psum);
                     pend = false;
                 }
             }
@@ -262,20 +243,21 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             const float mx = (-kdx * h0.z - kdy * h0.w) * ddelx_dx;
             const float my = (-kdy * h1.x - kdx * h0.w) * ddely_dy;
             const float gv[8] = {mx, my, fabsf(mx), fabsf(my), -0.5f * kdx * dx, -0.5f * kdx * dy, -0.5f * kdy * dy, u};
-#pragma unroll
-            for (int k = NGL; k < 8; ++k) pv[k - NGL] = gv[k];
-#pragma unroll
-            for (int k = 8 - NGL; k < NB; ++k) pv[k] = 0.f;  // butterfly padding
-            pend = NB > 0;
+            pend = kGeoSmem;
 
             // ---- channel gradients: lane c sums w[q] * gT[c][q] over the block's 32 pixels; lanes CT4.. sum the
             //      first NGL geometry terms the same way ----
-            const uint32_t wa = w_addr + parity * (uint32_t)((1 + NGL) * XROW * 4);
+            const uint32_t wa = w_addr + parity * (uint32_t)((1 + NX) * XROW * 4);
             parity ^= 1u;
             sts32(wa + lane * 4u, w);
 #pragma unroll
-            for (int k = 0; k < NGL; ++k) sts32(wa + (uint32_t)((1 + k) * XROW * 4) + lane * 4u, gv[k]);
+            for (int k = 0; k < NX; ++k) sts32(wa + (uint32_t)((1 + k) * XROW * 4) + lane * 4u, gv[k]);
             __syncwarp();
+            if constexpr (kGeoSmem) {
+                float4 ga[2];
+                lds128xN<2>(wa + (1u + (lane >> 2)) * (uint32_t)(XROW * 4) + (lane & 3u) * 32u, ga);
+                psum = ((ga[0].x + ga[0].y) + (ga[0].z + ga[0].w)) + ((ga[1].x + ga[1].y) + (ga[1].z + ga[1].w));
+            }
             const uint32_t wl = wa + my_array * (uint32_t)(XROW * 4);
             float cg[NPASS][4];
 #pragma unroll
@@ -302,28 +284,31 @@ __global__ void __launch_bounds__(32) render_bwd_kernel(const RenderParams p) {
             pgrec = grec;  // the geometry terms (pv) are reduced at the top of the next iteration
         }
     }
-    if constexpr (NB > 0) {
+    if constexpr (kGeoSmem) {
         if (pend) {
-            WarpTransposeReduce<NB, 16>::run(pv, lane);
-            constexpr int kShift = NB == 8 ? 2 : 3;
-            if ((lane & ((1u << kShift) - 1u)) == 0u && pv[0] != 0.f) atomicAdd(pgrec + CT4 + NGL + (lane >> kShift), pv[0]);
+            psum += __shfl_xor_sync(kFull, psum, 1);
+            psum += __shfl_xor_sync(kFull, psum, 2);
+            if ((lane & 3u) == 0u && psum != 0.f) atomicAdd(pgrec + CT4 + (lane >> 2), psum);
         }
     }
 }
 
-template <int CT4, int CHUNK>
+template <int CT4, int CHUNK, int MB>
 int launch_bwd_tc(const RenderParams& p, cudaStream_t stream, bool debug) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     const size_t smem = WarpStage<RS, CHUNK>::kSmemBytes;
     const long long blocks = (long long)p.grid_x * p.grid_y * 8;
-    render_bwd_kernel<CT4, CHUNK><<<(unsigned)blocks, 32, smem, stream>>>(p);
+    render_bwd_kernel<CT4, CHUNK, MB><<<(unsigned)blocks, 32, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
 
+// Rounds of 32 list entries while the idle lanes take the geometry terms; 16 from 28 channels on (shared memory per CTA
+// bounds the resident warps there).  At 28 channels 20 CTAs / SM are requested: ptxas otherwise settles on 118 registers.
 template <int CT4>
 int launch_bwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
-    return launch_bwd_tc<CT4, 32>(p, stream, debug);
+    if constexpr (CT4 <= 24) return launch_bwd_tc<CT4, 32, 0>(p, stream, debug);
+    else return launch_bwd_tc<CT4, 16, (CT4 == 28 ? 20 : 0)>(p, stream, debug);
 }
 
 }  // namespace
