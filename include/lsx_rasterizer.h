@@ -331,6 +331,26 @@ LSX_API int lsx_masked_l1_forward(int32_t C, int32_t H, int32_t W, int32_t mask_
 LSX_API int lsx_masked_l1_backward(int32_t C, int32_t H, int32_t W, int32_t mask_channels, const float* a, const float* b,
                                    const float* mask, const float* upstream, float* dL_da, void* stream);
 
+/* ---- next row (second half): 3-D neighbourhood regulariser of the language / instance features --------------
+ * loss_cls_3d(features = xyz (N,3), predictions (N,C), k, lambda_val, max_points, sample_size) of
+ * field_construction/utils/loss_utils.py:158-186 (called at field_construction/gaussian_field.py:461-465,482-485):
+ *   q = (predictions - min) / (max - min) over all elements (only if max > min); for each of the S sampled rows the k
+ *   nearest points (exact squared distances, the sample itself included, ties towards the lower index);
+ *   loss = lambda_val * mean over S*k*C of | q[s] * (log(q[s] + 1e-10) - log(q[nbr] + 1e-10)) |.
+ * The random choices of the reference (torch.randperm) stay with the caller: sample_idx is a DEVICE array of S row indices.
+ * forward : *loss (device scalar), nbr_idx (S,k) int32 and minmax[2] are written and must be handed to backward;
+ *           scratch = device buffer of lsx_cls3d_scratch_bytes() bytes (contents need not survive until backward).
+ * backward: dL_dpreds (N,C) fully written (zero rows for points that are neither sampled nor a neighbour), including the
+ *           gradient through min and max (split evenly among tied elements, like torch); upstream = DEVICE scalar (NULL = 1).
+ * 1 <= k <= 8 and k <= N, else -1.  No S x N distance matrix is materialised and the host never waits. */
+LSX_API int64_t lsx_cls3d_scratch_bytes(int32_t N, int32_t C, int32_t S, int32_t k);
+LSX_API int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
+                              const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax,
+                              void* scratch, void* stream);
+LSX_API int lsx_cls3d_backward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* preds,
+                               const int32_t* sample_idx, const int32_t* nbr_idx, const float* minmax, const float* upstream,
+                               float* dL_dpreds, void* scratch, void* stream);
+
 /* ---- next row: row pack / unpack for the on-disk formats ----------------------------------------------------
  * GaussianModel.save_ply / load_ply (field_construction/scene/gaussian_model.py:415-441,448-504) convert between the per-group
  * parameter tensors and one row of ncols floats per Gaussian.  rows[r * ncols + c] = arena[col_begin[c] + r * col_stride[c]]

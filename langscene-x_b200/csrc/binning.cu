@@ -13,25 +13,61 @@ namespace lsx {
 
 namespace {
 
+// Warp-cooperative expansion: a warp owns 32 consecutive depth-sorted Gaussians, whose pairs form ONE contiguous run of
+// the output (offsets are the exclusive scan in that order).  Lane j of each step writes output element j of the run
+// after locating its source Gaussian by a 5-step binary search over the lanes' run-local prefixes (shuffles), so every
+// store instruction covers 128 contiguous bytes.  (Thread-per-Gaussian emission wrote ~7 pairs per thread to 32
+// different runs per instruction: 9.3 M store sectors for 42 MB of payload, LSU-queue bound.)
 __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint32_t* __restrict__ sorted_idx,
                                                               const uint32_t* __restrict__ offsets,
                                                               const float2* __restrict__ means2D,
                                                               const int* __restrict__ radii, uint32_t grid_x,
                                                               uint32_t grid_y, uint32_t* __restrict__ tile_keys,
                                                               uint32_t* __restrict__ vals) {
+    constexpr unsigned kFull = 0xffffffffu;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P) return;
-    const uint32_t g = sorted_idx[k];
-    const int radius = radii[g];
-    if (!(radius > 0)) return;
-    uint32_t off = offsets[k];
-    uint2 rmin, rmax;
-    tile_rect(means2D[g], radius, rmin, rmax, grid_x, grid_y);
-    for (uint32_t y = rmin.y; y < rmax.y; ++y) {
-        for (uint32_t x = rmin.x; x < rmax.x; ++x) {
-            tile_keys[off] = y * grid_x + x;
-            vals[off] = g;
-            ++off;
+    const unsigned lane = threadIdx.x & 31u;
+    const int k0 = k - (int)lane;  // warp-uniform
+    if (k0 >= P) return;
+    uint32_t g = 0, w = 0, count = 0;
+    uint2 rmin = make_uint2(0u, 0u), rmax;
+    if (k < P) {
+        g = sorted_idx[k];
+        const int radius = radii[g];
+        if (radius > 0) {
+            tile_rect(means2D[g], radius, rmin, rmax, grid_x, grid_y);
+            w = rmax.x - rmin.x;
+            count = w * (rmax.y - rmin.y);
+        }
+    }
+    const uint32_t base = offsets[k0];
+    uint32_t pre = count;  // inclusive warp scan of the counts
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, pre, o);
+        if (lane >= (unsigned)o) pre += t;
+    }
+    const uint32_t total = __shfl_sync(kFull, pre, 31);
+    pre -= count;  // exclusive
+    for (uint32_t j0 = 0; j0 < total; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        // source = the last lane whose prefix is <= j (lanes without pairs share the prefix of their successor)
+        uint32_t s = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t ps = __shfl_sync(kFull, pre, (int)(s + step));
+            if (ps <= j) s += step;
+        }
+        const uint32_t sg = __shfl_sync(kFull, g, (int)s);
+        const uint32_t sw = __shfl_sync(kFull, w, (int)s);
+        const uint32_t sx = __shfl_sync(kFull, rmin.x, (int)s);
+        const uint32_t sy = __shfl_sync(kFull, rmin.y, (int)s);
+        const uint32_t sp = __shfl_sync(kFull, pre, (int)s);
+        if (j < total) {
+            const uint32_t t = j - sp;
+            const uint32_t row = t / sw, col = t - row * sw;  // row-major over the rectangle, y outer (duplicateWithKeys)
+            tile_keys[base + j] = (sy + row) * grid_x + (sx + col);
+            vals[base + j] = sg;
         }
     }
 }

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
     }
 }
 
-__global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+// 3 CTAs / SM (80 registers): measured 0.169 -> 0.151 ms for the two tile passes at C3 against 2 CTAs / SM; 4 spills
+__global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int n, int shift,
@@ -164,8 +165,10 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
     const int wbase = blockIdx.x * kTile + warp * (32 * kItems);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
-    uint32_t key[kItems];
-    uint32_t rank[kItems];
+    // keys AND values are fetched up front, 32 independent loads per thread in flight (fetching a value only when it
+    // is regrouped exposes one global-load latency per item: 40 % of this kernel's stall samples before the change)
+    uint32_t key[kItems], val[kItems];
+    uint32_t rank[kItems / 2];  // two 16-bit ranks per register (a warp segment holds 512 keys)
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int idx = wbase + i * 32 + lane;
@@ -174,18 +177,36 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int idx = wbase + i * 32 + lane;
-        const bool valid = idx < n;
-        const uint32_t d = valid ? ((key[i] >> shift) & mask) : 0x100u;
-        const uint32_t peers = __match_any_sync(kFull, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (lane == leader && valid) {
-            old = cnt[warp][d];
-            cnt[warp][d] = old + __popc(peers);
+        val[i] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
+    }
+    // ranking in groups of 8 items: the 8 warp matches of a group are independent and issue back to back; only the
+    // counter updates (leader lane per distinct digit) form a serial chain
+#pragma unroll
+    for (int g = 0; g < kItems; g += 8) {
+        uint32_t peers[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = wbase + (g + j) * 32 + lane;
+            const uint32_t d = idx < n ? ((key[g + j] >> shift) & mask) : 0x100u;
+            peers[j] = __match_any_sync(kFull, d);
         }
-        old = __shfl_sync(kFull, old, leader);
-        rank[i] = old + __popc(peers & lt_mask);
-        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int idx = wbase + (g + j) * 32 + lane;
+            const bool valid = idx < n;
+            const uint32_t d = (key[g + j] >> shift) & mask;
+            const int leader = __ffs(peers[j]) - 1;
+            uint32_t old = 0;
+            if (lane == leader && valid) {
+                old = cnt[warp][d];
+                cnt[warp][d] = old + __popc(peers[j]);
+            }
+            old = __shfl_sync(kFull, old, leader);
+            const uint32_t r = old + __popc(peers[j] & lt_mask);
+            if (j & 1) rank[(g + j) >> 1] |= r << 16;
+            else rank[(g + j) >> 1] = r;
+            __syncwarp();
+        }
     }
     __syncthreads();
     // per digit: block total -> block-local start (exclusive scan over digits), per-warp local starts, global start
@@ -213,9 +234,9 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(const uint32_t*
         const int idx = wbase + i * 32 + lane;
         if (idx < n) {
             const uint32_t d = (key[i] >> shift) & mask;
-            const uint32_t lp = cnt[warp][d] + rank[i];
+            const uint32_t lp = cnt[warp][d] + ((rank[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
             s_key[lp] = key[i];
-            s_val[lp] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            s_val[lp] = val[i];
         }
     }
     __syncthreads();

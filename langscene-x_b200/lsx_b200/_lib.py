@@ -131,6 +131,9 @@ EXPORTS = {
     "lsx_masked_l1_num_blocks": (c_int32, [ctypes.c_int64]),
     "lsx_masked_l1_forward": (c_int32, [c_int32, c_int32, c_int32, c_int32] + [c_void_p] * 5),
     "lsx_masked_l1_backward": (c_int32, [c_int32, c_int32, c_int32, c_int32] + [c_void_p] * 6),
+    "lsx_cls3d_scratch_bytes": (ctypes.c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "lsx_cls3d_forward": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_float] + [c_void_p] * 8),
+    "lsx_cls3d_backward": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_float] + [c_void_p] * 8),
     "lsx_rows_pack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_rows_unpack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),

@@ -4,6 +4,9 @@
   image_loss(image, gt, lambda_)    (1 - lambda_) * l1_loss(image, gt) + lambda_ * (1 - ssim(image, gt)), the combination at
                                     field_construction/gaussian_field.py:238-246, one kernel forward and one backward;
                                     returns (loss, l1, ssim_value) so that the loop can keep logging both terms.
+  masked_l1_loss(out, gt, mask)     the language-feature supervision (gaussian_field.py:450-451)
+  loss_cls_3d(xyz, feature, ...)    the 3-D neighbourhood regulariser (loss_utils.py:158-186): tiled exact k-NN of the sampled
+                                    rows + KL-style term, no (samples x N) distance matrix
 Gradients flow to the FIRST image only (the ground-truth image never requires grad in the reference).  No CPU path.
 """
 import ctypes
@@ -122,3 +125,75 @@ def masked_l1_loss(network_output, gt, mask=None):
     (1, H, W) bool or float (as Camera.get_language_feature returns it, field_construction/scene/cameras.py:137-151), or
     (C, H, W); None = plain l1_loss.  Gradient flows to `network_output` only."""
     return _MaskedL1.apply(network_output, gt, mask)
+
+
+class _Cls3d(torch.autograd.Function):
+    """lambda * mean |q[s] (log(q[s] + eps) - log(q[nbr] + eps))| for given sample rows; gradient to `predictions` only."""
+
+    @staticmethod
+    def forward(ctx, features, predictions, sample_idx, k, lambda_val):
+        N, C = predictions.shape
+        S = int(sample_idx.numel())
+        dev = predictions.device
+        pts, pred = features.detach().contiguous(), predictions.contiguous()
+        lib = _lib.load()
+        nbytes = int(lib.lsx_cls3d_scratch_bytes(N, C, S, k))
+        if nbytes <= 0:
+            raise RuntimeError(f"loss_cls_3d: need 1 <= k <= min(N, 8) and non-empty inputs (N={N}, C={C}, samples={S}, k={k})")
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        nbr = torch.empty((S, k), dtype=torch.int32, device=dev)
+        minmax = torch.empty(2, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lsx_cls3d_forward(N, C, S, k, float(lambda_val), pts.data_ptr(), pred.data_ptr(), sample_idx.data_ptr(),
+                                             loss.data_ptr(), nbr.data_ptr(), minmax.data_ptr(), scratch.data_ptr(),
+                                             _stream(dev)), "loss_cls_3d")
+        ctx.save_for_backward(pred, sample_idx, nbr, minmax)
+        ctx.k, ctx.lambda_val = k, float(lambda_val)
+        ctx.mark_non_differentiable(nbr)
+        return loss, nbr
+
+    @staticmethod
+    def backward(ctx, g, _g_nbr):
+        pred, sample_idx, nbr, minmax = ctx.saved_tensors
+        N, C = pred.shape
+        S, dev = int(sample_idx.numel()), pred.device
+        lib = _lib.load()
+        up = g.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()          # device scalar: no host read
+        scratch = torch.empty(int(lib.lsx_cls3d_scratch_bytes(N, C, S, ctx.k)), dtype=torch.uint8, device=dev)
+        out = torch.empty_like(pred)
+        with torch.cuda.device(dev):
+            _lib.check(lib.lsx_cls3d_backward(N, C, S, ctx.k, ctx.lambda_val, pred.data_ptr(), sample_idx.data_ptr(),
+                                              nbr.data_ptr(), minmax.data_ptr(), up.data_ptr(), out.data_ptr(),
+                                              scratch.data_ptr(), _stream(dev)), "loss_cls_3d backward")
+        return None, out, None, None, None
+
+
+def loss_cls_3d(features, predictions, k=5, lambda_val=2.0, max_points=200000, sample_size=800, *, sample_indices=None,
+                return_neighbors=False):
+    """Drop-in for loss_cls_3d of field_construction/utils/loss_utils.py:158-186 (the 3-D neighbourhood regulariser of the
+    language / instance features; called with features = xyz.detach(), predictions = the (N, C) feature parameter at
+    field_construction/gaussian_field.py:461-465,482-485): same positional signature, same random draws — the optional
+    down-sampling to `max_points` rows and the `sample_size` query rows both come from `torch.randperm(n)` on the CPU
+    generator, in the reference's order, so equal seeds select equal rows — but no (samples x N) distance matrix, no topk over
+    it and no host read of min / max: the k nearest neighbours are found by a tiled exact scan and the loss, its gradient
+    (including the part through the min / max normalisation) and the neighbour indices stay on the device.
+    `sample_indices` (1-D integer tensor) overrides the second draw; 1 <= k <= 8.  Gradient flows to `predictions` only."""
+    if not (features.is_cuda and predictions.is_cuda):
+        raise RuntimeError("loss_cls_3d: tensors must be CUDA tensors (this operator has no CPU path)")
+    if features.dim() != 2 or features.shape[1] != 3 or features.dtype != torch.float32:
+        raise RuntimeError("loss_cls_3d: features must be a float32 (N, 3) tensor of positions")
+    if predictions.dim() == 1:
+        predictions = predictions.unsqueeze(1)
+    if predictions.dim() != 2 or predictions.shape[0] != features.shape[0] or predictions.dtype != torch.float32:
+        raise RuntimeError("loss_cls_3d: predictions must be a float32 (N, C) tensor with one row per position")
+    if features.size(0) > max_points:                                   # loss_utils.py:160-163
+        indices = torch.randperm(features.size(0))[:max_points].to(features.device)
+        features = features[indices]
+        predictions = predictions[indices]
+    n = features.size(0)
+    if sample_indices is None:                                          # loss_utils.py:172
+        sample_indices = torch.randperm(n)[:sample_size]
+    idx = sample_indices.to(device=features.device, dtype=torch.int32).contiguous()
+    loss, nbr = _Cls3d.apply(features, predictions, idx, int(k), float(lambda_val))
+    return (loss, nbr) if return_neighbors else loss

@@ -112,9 +112,11 @@ def test_sh_degrees_rgb_only(deg):
 
 
 def test_precomputed_colors_and_cov():
-    import sys
-    sys.path.insert(0, os.path.join(hz.REPO, "oracle"))
-    from make_golden import cov_from_scene
+    import importlib.util   # by path: putting oracle/ itself on sys.path would shadow the `oracle` package
+    spec = importlib.util.spec_from_file_location("lsx_make_golden", os.path.join(hz.REPO, "oracle", "make_golden.py"))
+    make_golden = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(make_golden)
+    cov_from_scene = make_golden.cov_from_scene
     P, W, H, F = 15_000, 200, 160, 3
     scene, cam, grads = _scene(P, W, H, F, seed=9)
     cov = cov_from_scene(scene).to("cuda:0")
