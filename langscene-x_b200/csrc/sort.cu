@@ -12,8 +12,8 @@
 // the R duplicated pairs; the sorted output is identical (see binning.cu).  Both stages use this one
 // 32-bit-key kernel, as does the Morton sort of the KNN initialisation.
 //
-// Pass structure (8-bit digits): per-block digit histogram -> exclusive scan (digit-major) -> stable
-// scatter.  In the scatter kernel each warp owns a contiguous 512-key segment and ranks its keys with
+// Pass structure (8-bit digits): per-block digit histogram (+ digit and block-group totals by atomics) -> stable
+// scatter that derives its own offsets.  In the scatter kernel each warp owns a contiguous 512-key segment and ranks its keys with
 // __match_any_sync against warp-private shared-memory counters; a 256-thread step turns the per-warp
 // counters into block-local and global positions; the block's 4096 pairs are regrouped by digit in shared
 // memory and leave as contiguous runs (coalesced stores instead of 4-byte scatters).  No inter-block spinning anywhere (see B200_PROFILING.md on why).
@@ -114,13 +114,17 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __
 // ---------------------------------------------------------------------------------------------
 // radix sort pass
 // ---------------------------------------------------------------------------------------------
-// ghist == nullptr: digit-major per-block histogram hist[d * nb + b] (scanned by exclusive_scan_u32 afterwards).
-// ghist != nullptr: "short sort" mode for arrays of at most kShortSortBlocks blocks — block-major hist[b * 256 + d]
-// plus global digit totals in ghist[256]; the scatter kernel derives its offsets from these itself, so a pass is
-// two launches instead of five (sorts of <= 2 M keys are bound by launch latency, not bandwidth).
+// A pass is TWO launches, whatever the size (sorts on this path are bound by launch latency as much as by bandwidth):
+// the histogram kernel writes block-major per-block counts hist[b * 256 + d] and adds them, with global atomics, to
+// the digit totals gsum[d] and to the totals of its group of kGroup consecutive blocks gsum[256 * (1 + b / kGroup) + d];
+// the scatter kernel derives its own offsets: digit base (block scan of the totals) + earlier groups + earlier blocks
+// of its own group — at most nb / kGroup + kGroup - 1 coalesced 1-KB rows instead of a device-wide scan (3 more
+// launches) over the digit-major table.  No inter-block waiting anywhere.
+constexpr int kGroup = 64;
+
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
-                                                              uint32_t mask, uint32_t* __restrict__ hist, int nb,
-                                                              uint32_t* __restrict__ ghist) {
+                                                              uint32_t mask, uint32_t* __restrict__ hist,
+                                                              uint32_t* __restrict__ gsum) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -131,11 +135,11 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
         if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
     }
     __syncthreads();
-    if (ghist == nullptr) {
-        if (threadIdx.x <= mask) hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
-    } else {
-        hist[blockIdx.x * 256 + threadIdx.x] = h[threadIdx.x];
-        if (h[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], h[threadIdx.x]);
+    const uint32_t c = h[threadIdx.x];
+    hist[blockIdx.x * 256 + threadIdx.x] = c;
+    if (c) {
+        atomicAdd(&gsum[threadIdx.x], c);
+        atomicAdd(&gsum[256 * (1 + blockIdx.x / kGroup) + threadIdx.x], c);
     }
 }
 
@@ -144,19 +148,34 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int n, int shift,
-                                                                 uint32_t mask, const uint32_t* __restrict__ offsets,
-                                                                 int nb, const uint32_t* __restrict__ ghist) {
+                                                                 uint32_t mask, const uint32_t* __restrict__ hist,
+                                                                 const uint32_t* __restrict__ gsum) {
     __shared__ uint32_t cnt[kWarps][256];
     __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_key[kTile], s_val[kTile];   // the block's pairs regrouped by digit before they leave
+    __shared__ __align__(16) uint32_t s_key[kTile], s_val[kTile];   // the block's pairs regrouped by digit before they leave
     __shared__ uint32_t s_lstart[256], s_gbase[256];  // per digit: start inside the block / in the output array
-    uint32_t short_start = 0;  // short-sort mode: global position of this block's first key with digit threadIdx.x
-    if (ghist != nullptr) {
+    uint32_t my_start;  // global position of this block's first key with digit threadIdx.x
+    {
         uint32_t total;
-        const uint32_t digit_base = block_exclusive_scan(ghist[threadIdx.x], s_warp, total);
-        uint32_t before = 0;  // keys with this digit in earlier blocks (block-major histogram: coalesced over digits)
-        for (int b = 0; b < (int)blockIdx.x; ++b) before += offsets[b * 256 + threadIdx.x];
-        short_start = digit_base + before;
+        const uint32_t digit_base = block_exclusive_scan(gsum[threadIdx.x], s_warp, total);
+        // keys with each digit in earlier blocks = the earlier groups' totals + the earlier blocks of this group: a list
+        // of 1-KB rows, summed by four 64-thread row partitions with 16-B loads (<= (nb / kGroup + kGroup) / 4 loads per
+        // thread, 8 in flight), combined through s_key (not yet live)
+        const int grp = blockIdx.x / kGroup, in_grp = blockIdx.x - grp * kGroup;
+        const int part = threadIdx.x >> 6, col4 = threadIdx.x & 63;
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 8
+        for (int r = part; r < grp + in_grp; r += 4) {
+            const uint32_t* row = r < grp ? gsum + 256 * (1 + r) : hist + (size_t)(grp * kGroup + (r - grp)) * 256;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + col4);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+        }
+        reinterpret_cast<uint4*>(s_key)[part * 64 + col4] = acc;
+        __syncthreads();
+        my_start = digit_base + s_key[threadIdx.x] + s_key[256 + threadIdx.x] + s_key[512 + threadIdx.x] + s_key[768 + threadIdx.x];
     }
     for (int i = threadIdx.x; i < kWarps * 256; i += kThreads) (&cnt[0][0])[i] = 0;
     __syncthreads();
@@ -225,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
             run += t;
         }
         s_lstart[d] = lstart;
-        s_gbase[d] = d <= mask ? (ghist != nullptr ? short_start : offsets[d * nb + blockIdx.x]) : 0u;
+        s_gbase[d] = d <= mask ? my_start : 0u;
     }
     __syncthreads();
     // local shuffle: the block's keys (and values) land in shared memory grouped by digit, in stable order
@@ -272,41 +291,40 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out
     return 0;
 }
 
-constexpr int kShortSortBlocks = 512;  // <= 2 M keys
-constexpr int kMaxPasses = 4;          // 32-bit keys, 8-bit digits
+constexpr int kMaxPasses = 4;  // 32-bit keys, 8-bit digits
+
+static size_t gsum_words(int nb) { return (size_t)256 * (1 + ceil_div(nb, kGroup)); }
 
 size_t radix_sort_temp_bytes(int n) {
     const int nb = ceil_div(n > 0 ? n : 1, kTile);
-    return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + scan_temp_bytes(256 * nb) + kMaxPasses * 256 * sizeof(uint32_t);
+    return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + kMaxPasses * gsum_words(nb) * sizeof(uint32_t);
 }
 
 int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_bit, int end_bit, bool identity_vals,
                          void* temp, int* result_buf, cudaStream_t stream, bool debug) {
     *result_buf = 0;
     if (n <= 0) return 0;
+    if (radix_sort_num_passes(begin_bit, end_bit) > kMaxPasses) {
+        set_error("radix_sort_pairs_u32: more than %d passes requested (bits %d..%d)", kMaxPasses, begin_bit, end_bit);
+        return -1;
+    }
     const int nb = ceil_div(n, kTile);
     uint32_t* hist = static_cast<uint32_t*>(temp);
-    char* after_hist = static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256);
-    void* scan_temp = after_hist;
-    uint32_t* ghist_all = reinterpret_cast<uint32_t*>(after_hist + scan_temp_bytes(256 * nb));
-    const bool short_mode = nb <= kShortSortBlocks && radix_sort_num_passes(begin_bit, end_bit) <= kMaxPasses;
-    if (short_mode) LSX_CUDA_OK(cudaMemsetAsync(ghist_all, 0, kMaxPasses * 256 * sizeof(uint32_t), stream));
+    uint32_t* gsum_all = reinterpret_cast<uint32_t*>(static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256));
+    const size_t gw = gsum_words(nb);
+    LSX_CUDA_OK(cudaMemsetAsync(gsum_all, 0, kMaxPasses * gw * sizeof(uint32_t), stream));
     int cur = 0;
     bool first = true;
     int pass = 0;
     for (int shift = begin_bit; shift < end_bit; shift += 8, ++pass) {
         const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
         const uint32_t mask = (1u << bits) - 1u;
-        uint32_t* ghist = short_mode ? ghist_all + pass * 256 : nullptr;
-        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, nb, ghist);
+        uint32_t* gsum = gsum_all + pass * gw;
+        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
         LSX_KERNEL_OK(stream, debug);
-        if (!short_mode) {
-            int rc = exclusive_scan_u32(hist, nullptr, hist, (int)(mask + 1) * nb, nullptr, scan_temp, stream, debug);
-            if (rc) return rc;
-        }
         const uint32_t* vin = (first && identity_vals) ? nullptr : vals[cur];
         radix_scatter_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
-                                                          hist, nb, ghist);
+                                                          hist, gsum);
         LSX_KERNEL_OK(stream, debug);
         cur ^= 1;
         first = false;
