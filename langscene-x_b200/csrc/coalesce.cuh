@@ -17,15 +17,14 @@ namespace lsx {
 __host__ __device__ static inline int padded_row(int row_floats) { return row_floats | 1; }
 
 // global (rows x rowf, contiguous) -> smem (row stride srow).  `g` points at the slab's first element.
-// Four independent 16-B loads are issued per thread before any of them is consumed: these kernels are bound by
+// U (default four) independent 16-B loads are issued per thread before any of them is consumed: these kernels are bound by
 // memory latency (few resident warps because of the tile), so bytes in flight per thread is what matters.
-template <int NT>
+template <int NT, int U = 4>
 __device__ __forceinline__ void slab_load(float* __restrict__ s, const float* __restrict__ g, int rows, int rowf, int srow) {
     const int total = rows * rowf;
     const int tid = threadIdx.x;
     if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0 && rowf >= 4) {
         const int n4 = total >> 2;
-        constexpr int U = 4;
         for (int i0 = tid; i0 < n4; i0 += NT * U) {
             float4 v[U];
 #pragma unroll

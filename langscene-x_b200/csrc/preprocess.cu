@@ -105,7 +105,16 @@ __device__ __forceinline__ void ewa_frame(const float3 mean, const float fx, con
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int kPreFwdThreads = 128;
+#ifndef LSX_PRE_FWD_THREADS
+#define LSX_PRE_FWD_THREADS 128
+#endif
+#ifndef LSX_PRE_BWD_THREADS
+#define LSX_PRE_BWD_THREADS 128
+#endif
+constexpr int kPreFwdThreads = LSX_PRE_FWD_THREADS;
+// independent 16-B loads in flight per thread while the SH slab is fetched: the whole slab (12 per thread at degree 3) in
+// one round in the forward (C3: 0.190 -> 0.180 ms, C5: 0.88 -> 0.82); the backward is better off with 4 (0.238 vs 0.253)
+constexpr int kFwdSlabDepth = 12, kBwdSlabDepth = 4;
 // smem row stride of the record tile: 16-B aligned rows, and 12 t mod 32 distinct for 8 consecutive t => the
 // row owner's float4 accesses are conflict free
 __host__ __device__ static inline int record_tile_row(int rec_stride) { return rec_stride + 4; }
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const Pr
     float* s_rec = s_pre + ((kPreFwdThreads * sh_stride + 3) & ~3);
     const int b0 = blockIdx.x * kPreFwdThreads;
     const int rows = min(kPreFwdThreads, p.P - b0);
-    if (p.shs && p.colors_precomp == nullptr) slab_load<kPreFwdThreads>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_stride);
+    if (p.shs && p.colors_precomp == nullptr) slab_load<kPreFwdThreads, kFwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_stride);
     int c = REC_HEAD + 3;
     if (p.include_feature) {
         slab_load<kPreFwdThreads>(s_rec + c, p.language_feature + (size_t)b0 * p.F, rows, p.F, rec_row);
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const Pr
 // with dL/dsh at the end; `grec` is its packed gradient record from the tile backward pass (render_bwd.cu):
 // [rgb(3) | language(F) | instance(Fi) | all_map(5) | pad | mean2D.xy, |mean2D|.xy, conic.xyw, opacity].
 // Culled splats have an all-zero record (memset, never accumulated into).
-constexpr int kPreBwdThreads = 128;
+constexpr int kPreBwdThreads = LSX_PRE_BWD_THREADS;
 
 __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, float* __restrict__ sh_row,
                                                    const float* __restrict__ grec) {
@@ -604,8 +613,8 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
     float* s_rec = s_pre + (p.shs ? kPreBwdThreads * sh_row : 0);
     const int b0 = blockIdx.x * kPreBwdThreads;
     const int rows = min(kPreBwdThreads, p.P - b0);
-    if (p.shs) slab_load<kPreBwdThreads>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
-    slab_load<kPreBwdThreads>(s_rec, p.grad_records + (size_t)b0 * p.grad_stride, rows, p.grad_stride, rec_row);
+    if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
+    slab_load<kPreBwdThreads, kBwdSlabDepth>(s_rec, p.grad_records + (size_t)b0 * p.grad_stride, rows, p.grad_stride, rec_row);
     __syncthreads();
     if ((int)threadIdx.x < rows)
         preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, s_rec + threadIdx.x * rec_row);
