@@ -35,10 +35,11 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/)
-NCU_TRAFFIC = {"render_bwd": 611455744, "render_fwd": 373092096}
-# smsp__issue_active.avg.pct_of_peak_sustained_active of the same captures: what actually bounds these kernels
-NCU_ISSUE_BUSY_PCT = {"render_bwd": 69.6, "render_fwd": 92.3}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+# (profiles/r4l_ncu_kernels.md: the kernels as shipped at the end of round 1)
+NCU_TRAFFIC = {"render_bwd": 612417792, "render_fwd": 372893696}
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture: what actually bounds these kernels
+NCU_ISSUE_BUSY_PCT = {"render_bwd": 76.0, "render_fwd": 92.3}
 
 
 def load_peaks():

@@ -1,5 +1,5 @@
 """Summarise an .ncu-rep (ncu --set full) as a markdown table of the metrics DESIGN.md / bench.py quote.
-Usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep > profiles/x.md"""
+Usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-name regex] > profiles/x.md"""
 import csv
 import io
 import subprocess
@@ -35,6 +35,9 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if len(sys.argv) > 2:
+        import re
+        data = [r for r in data if re.search(sys.argv[2], r[hdr.index("Kernel Name")])]
     names = [r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")[-60:] for r in data]
     print(f"# ncu --set full summary of `{rep.split('/')[-1]}`\n")
     print("| metric | " + " | ".join(names) + " |")
