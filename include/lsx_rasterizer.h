@@ -43,7 +43,7 @@ extern "C" {
 #define LSX_API
 #endif
 
-#define LSX_ABI_VERSION 3
+#define LSX_ABI_VERSION 4
 #define LSX_MAX_BLEND_CHANNELS 40 /* 3 + F + Fi + 5 must not exceed this */
 
 /* scratch allocation callback: must return a device pointer to at least `bytes` bytes, aligned to
@@ -386,6 +386,11 @@ typedef struct lsx_scratch_layout {
     size_t point_list;     /* u32[R] sorted Gaussian indices */
     size_t binning_bytes;
     size_t masks;          /* u8[R]  sub-tile footprint mask per list entry (binning buffer) */
+    /* ABI v4: the per-block compacted lists the render kernels walk (built from the masks) */
+    size_t blk_list;       /* u32[8*R] binning buffer: for block w (8x4 pixels) of tile t, the positions inside the tile's range
+                            *          of the entries with mask bit w set, in list order, at [w*R + ranges[t].start + k] */
+    size_t blk_cnt;        /* u32[8*tiles] binning buffer: list lengths, [8*t + w] */
+    size_t k_contrib;      /* u32[W*H] image buffer: elements of the pixel's block list up to its last contributor */
 } lsx_scratch_layout;
 
 LSX_API int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,

@@ -140,6 +140,7 @@ struct ImageScratch {
     float* final_T;
     uint32_t* n_contrib;
     uint2* ranges;
+    uint32_t* k_contrib;  // per pixel: length of its block's compacted list up to its last contributor (render_fwd -> render_bwd)
     size_t bytes;
 };
 
@@ -152,11 +153,14 @@ ImageScratch carve_image(char* base, int W, int H, lsx_scratch_layout* lay) {
     s.final_T = c.take<float>(n, &o0);
     s.n_contrib = c.take<uint32_t>(n, &o1);
     s.ranges = c.take<uint2>(tiles, &o2);
+    size_t ok = 0;
+    s.k_contrib = c.take<uint32_t>(n, &ok);
     s.bytes = c.total();
     if (lay) {
         lay->final_T = o0;
         lay->n_contrib = o1;
         lay->ranges = o2;
+        lay->k_contrib = ok;
         lay->image_bytes = s.bytes;
     }
     return s;
@@ -168,10 +172,12 @@ struct BinningScratch {
     uint32_t* vals_alt;
     uint32_t* tile_keys[2];
     void* sort_temp;
+    uint32_t* blk_list;  // 8 x R: per 8x4 block of every tile, the compacted list of its entries (cull.cu); stride R
+    uint32_t* blk_cnt;   // 8 per tile
     size_t bytes;
 };
 
-BinningScratch carve_binning(char* base, int R, lsx_scratch_layout* lay) {
+BinningScratch carve_binning(char* base, int R, int num_tiles, lsx_scratch_layout* lay) {
     BinningScratch s{};
     Carver c(base);
     const size_t r = (size_t)(R > 0 ? R : 0);
@@ -183,11 +189,16 @@ BinningScratch carve_binning(char* base, int R, lsx_scratch_layout* lay) {
     s.tile_keys[0] = c.take<uint32_t>(r);
     s.tile_keys[1] = c.take<uint32_t>(r);
     s.sort_temp = c.take<char>(radix_sort_temp_bytes(R));
+    size_t obl = 0, obc = 0;
+    s.blk_list = c.take<uint32_t>(8 * r, &obl);
+    s.blk_cnt = c.take<uint32_t>(8 * (size_t)(num_tiles > 0 ? num_tiles : 0), &obc);
     s.bytes = c.total() + kAlign;
     if (lay) {
         lay->point_list = o0;
         lay->binning_bytes = s.bytes;
         lay->masks = om;
+        lay->blk_list = obl;
+        lay->blk_cnt = obc;
     }
     return s;
 }
@@ -241,7 +252,7 @@ int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R, int32_t
     GeomScratch g = carve_geom(nullptr, P, record_stride(n_blend_channels));
     *out = g.lay;
     carve_image(nullptr, W, H, out);
-    carve_binning(nullptr, R, out);
+    carve_binning(nullptr, R, ceil_div(W, TILE_X) * ceil_div(H, TILE_Y), out);
     return 0;
 }
 
@@ -364,13 +375,13 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     }
     const int R = (int)R_host;
 
-    BinningScratch bn = carve_binning(nullptr, R, nullptr);
+    BinningScratch bn = carve_binning(nullptr, R, num_tiles, nullptr);
     char* bbase = a->binning_alloc(a->binning_user, bn.bytes);
     if (!bbase) {
         set_error("lsx_rasterize_forward: binning scratch allocation failed");
         return -4;
     }
-    bn = carve_binning(bbase, R, nullptr);
+    bn = carve_binning(bbase, R, num_tiles, nullptr);
 
     // ---- K3/K4/K5: emit (tile, idx) pairs in depth order, stable tile sort, tile ranges -----------
     const int tile_bits = bits_for((uint32_t)num_tiles);
@@ -398,7 +409,8 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
         if (rc) return rc;
         {
             StageTimer _t(LSX_STAGE_FOOTPRINT_MASKS, stream);
-            rc = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, stream, debug);
+            rc = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, bn.blk_list,
+                                        (size_t)R, bn.blk_cnt, stream, debug);
         }
         if (rc) return rc;
     } else {
@@ -412,6 +424,7 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
     rp.n_channels = nch; rp.rec_stride = rs;
     rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
+    rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
     rp.bg = a->background;
     rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
     rp.out_color = a->out_color; rp.out_language_feature = a->out_language_feature;
@@ -465,7 +478,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     const int rs = record_stride(nch);
     GeomScratch gm = carve_geom(const_cast<char*>(a->geom_buffer), P, rs);
     ImageScratch im = carve_image(const_cast<char*>(a->image_buffer), W, H, nullptr);
-    BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), R, nullptr);
+    BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), R, (int)(grid_x * grid_y), nullptr);
 
     const int gs = round_up4(nch) + 8;  // floats per packed gradient record
     {
@@ -480,6 +493,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
         rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
         rp.n_channels = nch; rp.rec_stride = rs;
         rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
+        rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
         rp.bg = a->background;
         rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
         rp.dL_dout_color = a->dL_dout_color; rp.dL_dout_language_feature = a->dL_dout_language_feature;
@@ -547,8 +561,8 @@ int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_
     }
     GeomScratch gm = carve_geom(const_cast<char*>(geom_buffer), P, record_stride(n_blend_channels));
     ImageScratch im = carve_image(const_cast<char*>(image_buffer), W, H, nullptr);
-    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), R, nullptr);
     const int tiles = ceil_div(W, TILE_X) * ceil_div(H, TILE_Y);
+    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), R, tiles, nullptr);
     return launch_debug_keys(tiles, im.ranges, bn.point_list, gm.depths, keys_out, static_cast<cudaStream_t>(stream));
 }
 

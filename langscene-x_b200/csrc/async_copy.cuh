@@ -46,4 +46,15 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                  : "memory");
 }
 
+// ---- per-thread asynchronous 16-B copies (cp.async -> SASS LDGSTS): unlike the bulk copy, whose operands live in
+// uniform registers (one elected lane per copy), every lane supplies its own source / destination.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 }  // namespace lsx

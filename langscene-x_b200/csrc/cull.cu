@@ -1,4 +1,4 @@
-// cull.cu — per-(tile, list entry) sub-tile footprint masks.
+// cull.cu — per-(tile, list entry) sub-tile footprint masks and the per-block compacted lists built from them.
 //
 // The reference tests every list entry of a tile against every pixel of the tile
 // (forward.cu:335-407, backward.cu:524-676): an entry is blended at a pixel only if
@@ -83,27 +83,77 @@ __device__ __forceinline__ unsigned footprint_mask(const float mx, const float m
     return m;
 }
 
+// One CTA per tile.  Besides the mask byte per list entry (kept: tests and the layout query read it) the kernel writes,
+// for each of the tile's eight 8x4 blocks, the COMPACTED list of the entries whose bit is set — their positions inside the
+// tile's range, in list (= depth) order — at blk_list[w * list_stride + range.x ...] and its length at blk_cnt[8 tile + w].
+// The render kernels walk these lists (tile_stage.cuh: ListStage): full 16-entry rounds, no per-round mask / ballot work.
+// Ordered compaction per 256-entry chunk: 8 warp ballots give the warp totals (lane w keeps bit w's), a 64-word exchange
+// turns them into per-warp bases (lanes 0..7), a second round of ballots places every set bit.
 __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __restrict__ ranges,
                                                               const uint32_t* __restrict__ point_list,
                                                               const float* __restrict__ records, int rec_stride,
-                                                              uint32_t grid_x, uint8_t* __restrict__ masks) {
+                                                              uint32_t grid_x, uint8_t* __restrict__ masks,
+                                                              uint32_t* __restrict__ blk_list, size_t list_stride,
+                                                              uint32_t* __restrict__ blk_cnt) {
+    constexpr unsigned kFull = 0xffffffffu;
+    __shared__ uint32_t s_cnt[8][8];  // [warp][block]
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
+    const uint32_t n = r.y - r.x;
     const float tx0 = (float)((tile % grid_x) * TILE_X), ty0 = (float)((tile / grid_x) * TILE_Y);
-    for (uint32_t i = r.x + threadIdx.x; i < r.y; i += blockDim.x) {
-        const float* rec = records + (size_t)point_list[i] * rec_stride;
-        const float4 h0 = __ldg(reinterpret_cast<const float4*>(rec));
-        const float2 h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
-        masks[i] = (uint8_t)footprint_mask(h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, tx0, ty0);
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t run = 0;  // lanes 0..7 (of every warp): entries of block `lane` emitted by earlier chunks
+    for (uint32_t base = 0; base < n; base += 256) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned m = 0u;
+        if (i < n) {
+            const float* rec = records + (size_t)point_list[r.x + i] * rec_stride;
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(rec));
+            const float2 h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
+            m = footprint_mask(h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, tx0, ty0);
+            masks[r.x + i] = (uint8_t)m;
+        }
+        uint32_t wtotal = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t t = __popc(__ballot_sync(kFull, (m >> w) & 1u));
+            if (lane == (unsigned)w) wtotal = t;
+        }
+        if (lane < 8) s_cnt[warp][lane] = wtotal;
+        __syncthreads();
+        uint32_t wbase = 0;
+        if (lane < 8) {
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; ++w2) {
+                const uint32_t c = s_cnt[w2][lane];
+                before += ((unsigned)w2 < warp) ? c : 0u;
+                total += c;
+            }
+            wbase = run + before;
+            run += total;
+        }
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const bool set = ((m >> w) & 1u) != 0u;
+            const unsigned bal = __ballot_sync(kFull, set);
+            const uint32_t b0 = __shfl_sync(kFull, wbase, w);
+            if (set) blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal & lt)] = i;
+        }
+        __syncthreads();  // s_cnt is rewritten by the next chunk
     }
+    if (warp == 0 && lane < 8) blk_cnt[8 * tile + lane] = run;
 }
 
 }  // namespace
 
 int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,
-                           int rec_stride, uint32_t grid_x, uint8_t* masks, cudaStream_t stream, bool debug) {
+                           int rec_stride, uint32_t grid_x, uint8_t* masks, uint32_t* blk_list, size_t list_stride,
+                           uint32_t* blk_cnt, cudaStream_t stream, bool debug) {
     if (num_tiles <= 0) return 0;
-    footprint_masks_kernel<<<num_tiles, 256, 0, stream>>>(ranges, point_list, records, rec_stride, grid_x, masks);
+    footprint_masks_kernel<<<num_tiles, 256, 0, stream>>>(ranges, point_list, records, rec_stride, grid_x, masks, blk_list,
+                                                         list_stride, blk_cnt);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

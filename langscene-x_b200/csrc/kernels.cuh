@@ -103,7 +103,8 @@ int launch_emit_tile_pairs(int P, const uint32_t* sorted_idx, const uint32_t* of
 int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, int num_tiles, cudaStream_t stream,
                        bool debug);
 int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,
-                           int rec_stride, uint32_t grid_x, uint8_t* masks, cudaStream_t stream, bool debug);
+                           int rec_stride, uint32_t grid_x, uint8_t* masks, uint32_t* blk_list, size_t list_stride,
+                           uint32_t* blk_cnt, cudaStream_t stream, bool debug);
 int launch_debug_keys(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* depths,
                       uint64_t* keys_out, cudaStream_t stream);
 
@@ -119,6 +120,14 @@ struct RenderParams {
     const uint2* ranges;
     const uint32_t* point_list;
     const uint8_t* masks;  // per list entry: bit w set iff the splat may blend inside block w of its tile (cull.cu)
+    // per 8x4 block w of tile t: the positions (inside the tile's range) of the entries with bit w set, in list order, at
+    // blk_list[w * list_stride + ranges[t].x + k], k < blk_cnt[8 t + w]  (cull.cu)
+    const uint32_t* blk_list;
+    size_t list_stride;
+    const uint32_t* blk_cnt;
+    // per pixel: number of elements of its block's compacted list up to and including its last contributor (forward ->
+    // backward; n_contrib keeps the reference's meaning: position in the tile list + 1)
+    uint32_t* k_contrib;
     const float* records;
     const float* bg;
     // forward outputs / backward inputs

@@ -15,9 +15,9 @@
 //     s = <feat[g], dL/dpix>, and dL/dalpha = (s - B_behind) * T.  That removes 2*Ct registers and ~3*Ct flops
 //     per blend compared with the per-channel form.  (Its rounding differs from the reference's per-channel
 //     differences by O(1e-7 |s| / |s - B|); see the tolerance note in tests/test_parity_gpu.py.)
-//   * ONE WARP PER CTA: warp = one 8x4 pixel block of a tile; it stages (TMA, double-buffered, tile_stage.cuh)
-//     and visits only the list entries whose footprint-mask bit for its block is set (cull.cu), back to front,
-//     starting below the block's deepest contributor.  No CTA-wide barrier anywhere.
+//   * ONE WARP PER CTA: warp = one 8x4 pixel block of a tile; it walks its block's compacted list (cull.cu; staged by
+//     per-lane asynchronous copies, double-buffered, tile_stage.cuh: ListStage) back to front, starting below the
+//     block's deepest contributor (render_fwd.cu leaves every pixel's depth in list elements).  No CTA-wide barrier.
 //   * the channel gradients of one entry, dL/dfeat[c] = sum_pix (alpha T)_pix * dL/dpix[c], are an outer
 //     product over the warp's 32 pixels.  Each lane keeps TWO views of the block's upstream gradient in
 //     registers: its own pixel's channel vector (for s) and, transposed, channel `lane` of all 32 pixels.
@@ -92,7 +92,7 @@ __device__ __forceinline__ void load_pixel_gradients(const RenderParams& p, cons
 
 }
 
-template <int CT4, int CHUNK, int MB>
+template <int CT4, int MB>
 __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     constexpr int GS = CT4 + 8;                // floats per packed gradient record
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     constexpr bool kGeoSmem = (NGL == 0);
     constexpr int NX = 8;                      // geometry arrays exchanged through smem
     constexpr int XROW = 36;                   // floats between exchanged arrays: 16-B aligned, bank offset 4 per array
-    using Stage = WarpStage<RS, CHUNK>;
+    using Stage = ListStage<RS>;
+    constexpr int CHUNK = Stage::CHUNK;
     static_assert(Stage::kIdsOff >= 32 * TS * 4, "transposition scratch must fit in the record buffers");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -131,14 +132,16 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     // ---- per-pixel state -------------------------------------------------------------------------
     const float T_final = inside ? p.final_T[pix] : 0.f;
     float T = T_final;
-    const int last_contributor = inside ? (int)p.n_contrib[pix] : 0;
+    // this pixel's contributors are the first last_k elements of its block's compacted list (render_fwd.cu)
+    const int last_k = inside ? (int)p.k_contrib[pix] : 0;
 
     float g[CT4];  // upstream gradient of every blended channel of this pixel
     float bg_dot = 0.f;
     load_pixel_gradients<CT4>(p, inside, pix, HW, pxf, pyf, g, bg_dot);
 
     // deepest contributor of the block: list entries at or beyond it are never blended by any of its pixels
-    const int n_eff = min(__reduce_max_sync(kFull, last_contributor), n);
+    const int cnt = (n > 0) ? (int)p.blk_cnt[8 * tile + warp] : 0;
+    const int n_eff = min(__reduce_max_sync(kFull, last_k), cnt);
     if (n_eff == 0) return;
 
     // ---- transposed view: gT[ps][q] = upstream gradient of channel (32 ps + lane) at pixel q of this block ----
@@ -159,7 +162,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     // which exchanged array this lane sums in the outer-product phase: 0 = weights, 1 + k = geometry term k
     const uint32_t my_array = ((int)lane >= CT4 && (int)lane < CT4 + NGL) ? (1u + lane - CT4) : 0u;
     Stage stage;
-    stage.init(smem_raw);
     const int nrounds = (n_eff + CHUNK - 1) / CHUNK;
 
     float Bacc = 0.f;  // <colour accumulated behind the current entry (inclusive), upstream gradient>
@@ -171,29 +173,18 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     float* pgrec = nullptr;
     bool pend = false;    // warp-uniform
 
-    // round r covers list indices n_eff-1 - (r*CHUNK + lane), i.e. back to front
-    auto entry_of = [&](int r) -> long long {
-        const int e = n_eff - 1 - (r * CHUNK + (int)lane);
-        return (lane < CHUNK && e >= 0) ? (long long)range.x + e : -1;
-    };
-
-    stage.prefetch(entry_of(0), p.point_list, p.masks);
-    unsigned bits_next = stage.issue(0, warp, p.records);
-    stage.prefetch(entry_of(1), p.point_list, p.masks);
+    // back to front over the compacted list: round r covers elements n_eff-1 - (16 r + slot)
+    stage.start(smem_raw, p.blk_list + (size_t)warp * p.list_stride + range.x, p.point_list + range.x, p.records,
+                n_eff - 1, -1, n_eff);
     for (int r = 0; r < nrounds; ++r) {
-        unsigned bits = bits_next;
-        if (r + 1 < nrounds) {
-            bits_next = stage.issue((r + 1) & 1, warp, p.records);
-            stage.prefetch(entry_of(r + 2), p.point_list, p.masks);
-        }
-        stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
+        stage.advance(r);
+        const int m = stage.round_size(r);
         uint32_t ra = stage.rec_addr(r & 1) - Stage::kRecBytes;
         uint32_t ia = stage.ids_addr(r & 1) - 4;
-        const int e0 = n_eff - 1 - r * CHUNK;  // list index of lane 0's candidate
+        const int k0 = n_eff - 1 - r * CHUNK;  // list element of slot 0
 
-        while (bits) {
-            const int e = e0 - (__ffs(bits) - 1);
-            bits &= bits - 1;
+        for (int s_ = 0; s_ < m; ++s_) {
+            const int e = k0 - s_;
             ra += Stage::kRecBytes;
             ia += 4;
             const float4 h0 = lds128(ra);
@@ -212,7 +203,7 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
             const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
             const float G = expf(power);
             const float alpha = splat_alpha(h1.y, G);
-            const bool blend = (e < last_contributor) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+            const bool blend = (e < last_k) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
             if (__ballot_sync(kFull, blend) == 0) continue;
 
             // per-lane terms; lanes that do not blend carry u = w = 0 so that every product below vanishes
@@ -284,6 +275,7 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
             pgrec = grec;  // the geometry terms (pv) are reduced at the top of the next iteration
         }
     }
+    stage.drain();
     if constexpr (kGeoSmem) {
         if (pend) {
             psum += __shfl_xor_sync(kFull, psum, 1);
@@ -293,22 +285,16 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     }
 }
 
-template <int CT4, int CHUNK, int MB>
-int launch_bwd_tc(const RenderParams& p, cudaStream_t stream, bool debug) {
-    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    const size_t smem = WarpStage<RS, CHUNK>::kSmemBytes;
-    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
-    render_bwd_kernel<CT4, CHUNK, MB><<<(unsigned)blocks, 32, smem, stream>>>(p);
-    LSX_KERNEL_OK(stream, debug);
-    return 0;
-}
-
-// Rounds of 32 list entries while the idle lanes take the geometry terms; 16 from 28 channels on (shared memory per CTA
-// bounds the resident warps there).  At 28 channels 20 CTAs / SM are requested: ptxas otherwise settles on 118 registers.
+// At 28 channels 20 CTAs / SM are requested: ptxas otherwise settles on more registers than the 96 that fit.
 template <int CT4>
 int launch_bwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
-    if constexpr (CT4 <= 24) return launch_bwd_tc<CT4, 32, 0>(p, stream, debug);
-    else return launch_bwd_tc<CT4, 16, (CT4 == 28 ? 20 : 0)>(p, stream, debug);
+    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    constexpr int MB = (CT4 == 28) ? 20 : 0;
+    const size_t smem = ListStage<RS>::kSmemBytes;
+    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
+    render_bwd_kernel<CT4, MB><<<(unsigned)blocks, 32, smem, stream>>>(p);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
 }
 
 }  // namespace

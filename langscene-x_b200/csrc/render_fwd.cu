@@ -11,18 +11,16 @@
 //   * ONE WARP PER CTA: warp = one 8x4 pixel block of a 16x16 tile (32-B row segments -> whole-sector image
 //     stores); 8 consecutive CTAs share a tile list.  No CTA-wide barrier exists, finished blocks free their
 //     slot immediately, and up to 32 blocks are resident per SM;
-//   * each warp stages only the list entries whose footprint-mask bit for its block is set (cull.cu,
-//     tile_stage.cuh): ~70 % of the (block, entry) pairs of the reference's loop are never touched.  Staging is
-//     done by the TMA engine, one contiguous sector-aligned record per entry holding xy/conic/opacity AND all
-//     blended channels, double-buffered so the copies overlap blending; the blend loop reads them as
-//     warp-broadcast LDS.128;
+//   * each warp walks its block's COMPACTED list — the entries whose footprint reaches the block (cull.cu,
+//     tile_stage.cuh: ListStage): ~70 % of the (block, entry) pairs of the reference's loop are never touched and
+//     every 16-entry round is full.  Staging: per-lane 16-B asynchronous copies (two lanes per record) of one
+//     contiguous sector-aligned record per entry holding xy/conic/opacity AND all blended channels,
+//     double-buffered so the copies overlap blending; the blend loop reads them as warp-broadcast LDS.128;
 //   * no per-pixel `done` flag: a terminated pixel continues with T = 0, for which the reference's own
 //     test (T (1 - alpha) < 1e-4) keeps failing, and its final transmittance is parked in a second
 //     register; the out_observe count is warp-aggregated (one integer atomic per warp and entry);
 //   * thresholds (alpha < 1/255, T < 1e-4, T > 0.5) use the same fp32 expressions and full-precision
 //     expf as the reference so that n_contrib / final_T / out_observe are reproduced exactly.
-#include <cstdlib>
-
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
@@ -32,21 +30,12 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-inline int tune_chunk() {  // LSX_FWD_CHUNK=32 selects the 32-entry rounds (experiments only)
-    static const int v = [] {
-        const char* e = getenv("LSX_FWD_CHUNK");
-        return e ? atoi(e) : 16;
-    }();
-    return v;
-}
-
-template <int CT4, int CHUNK>
+template <int CT4>
 __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    using Stage = WarpStage<RS, CHUNK>;
+    using Stage = ListStage<RS>;
+    constexpr int CHUNK = Stage::CHUNK;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Stage stage;
-    stage.init(smem_raw);
 
     const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -56,83 +45,67 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
 
+    // this block's compacted list: the entries of the tile's range whose footprint reaches the block (cull.cu)
     const uint2 range = p.ranges[tile];
-    const int n = (int)(range.y - range.x);
-    const int nrounds = (n + CHUNK - 1) / CHUNK;
+    const int cnt = (range.y > range.x) ? (int)p.blk_cnt[8 * tile + warp] : 0;
+    const uint32_t* list = p.blk_list + (size_t)warp * p.list_stride + range.x;
+    const int nrounds = (cnt + CHUNK - 1) / CHUNK;
 
     // A live pixel carries its transmittance in T.  When the reference would set `done`, T is parked in
     // T_final and T becomes 0: from then on T * (1 - alpha) < 1e-4 holds for every candidate, i.e. the
     // pixel keeps "terminating" without any state change — exactly the reference's behaviour of ignoring it.
     float T = inside ? 1.0f : 0.0f;
     float T_final = 1.0f;
-    uint32_t last_contributor = 0;
+    uint32_t last_k = 0;  // elements of the compacted list up to and including this pixel's last contributor
     float acc[CT4];
 #pragma unroll
     for (int c = 0; c < CT4; ++c) acc[c] = 0.f;
 
-    auto entry_of = [&](int r) -> long long {
-        const int e = r * CHUNK + lane;
-        return (lane < CHUNK && e < n) ? (long long)range.x + e : -1;
-    };
-
-    unsigned bits_next = 0;
-    int issued = 0, consumed = 0;
-    if (nrounds > 0 && !__all_sync(kFull, T == 0.0f)) {
-        stage.prefetch(entry_of(0), p.point_list, p.masks);
-        bits_next = stage.issue(0, warp, p.records);
-        issued = 1;
-        stage.prefetch(entry_of(1), p.point_list, p.masks);
-    }
-    for (int r = 0; r < issued; ++r) {
-        unsigned bits = bits_next;
-        if (r + 1 < nrounds) {
-            bits_next = stage.issue((r + 1) & 1, warp, p.records);
-            issued = r + 2;
-            stage.prefetch(entry_of(r + 2), p.point_list, p.masks);
-        }
-        stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
-        consumed = r + 1;
-
-        uint32_t ra = stage.rec_addr(r & 1);
-        uint32_t ia = stage.ids_addr(r & 1);
-        while (bits) {
-            const int pos = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const float4 h0 = lds128(ra);      // x, y, conic.x, conic.y
-            const float2 h1 = lds64(ra + 16);  // conic.z, opacity
-            const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
-            const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-            const float alpha = splat_alpha(h1.y, expf(power));
-            const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
-            const bool cand = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            const bool blend = cand && !(test_T < 0.0001f);
-            if (cand && !blend && T != 0.0f) {  // the reference's `done = true` (entry NOT blended)
-                T_final = T;
-                T = 0.0f;
-            }
-            const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
-            if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
-            if (blend) {
-                const float w = alpha * T;
-                float4 f[CT4 / 4];
-                lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
-#pragma unroll
-                for (int q = 0; q < CT4 / 4; ++q) {
-                    acc[4 * q + 0] += f[q].x * w;
-                    acc[4 * q + 1] += f[q].y * w;
-                    acc[4 * q + 2] += f[q].z * w;
-                    acc[4 * q + 3] += f[q].w * w;
+    Stage stage;
+    const bool any_live = !__all_sync(kFull, T == 0.0f);
+    if (nrounds > 0 && any_live) {
+        stage.start(smem_raw, list, p.point_list + range.x, p.records, 0, 1, cnt);
+        for (int r = 0; r < nrounds; ++r) {
+            stage.advance(r);
+            const int m = stage.round_size(r);
+            uint32_t ra = stage.rec_addr(r & 1);
+            uint32_t ia = stage.ids_addr(r & 1);
+            for (int s_ = 0; s_ < m; ++s_) {
+                const float4 h0 = lds128(ra);      // x, y, conic.x, conic.y
+                const float2 h1 = lds64(ra + 16);  // conic.z, opacity
+                const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
+                const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
+                const float alpha = splat_alpha(h1.y, expf(power));
+                const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -alpha));
+                const bool cand = !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                const bool blend = cand && !(test_T < 0.0001f);
+                if (cand && !blend && T != 0.0f) {  // the reference's `done = true` (entry NOT blended)
+                    T_final = T;
+                    T = 0.0f;
                 }
-                T = test_T;
-                last_contributor = (uint32_t)(r * CHUNK + pos + 1);
+                const unsigned om = __ballot_sync(kFull, blend && (T > 0.5f));
+                if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
+                if (blend) {
+                    const float w = alpha * T;
+                    float4 f[CT4 / 4];
+                    lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
+#pragma unroll
+                    for (int q = 0; q < CT4 / 4; ++q) {
+                        acc[4 * q + 0] += f[q].x * w;
+                        acc[4 * q + 1] += f[q].y * w;
+                        acc[4 * q + 2] += f[q].z * w;
+                        acc[4 * q + 3] += f[q].w * w;
+                    }
+                    T = test_T;
+                    last_k = (uint32_t)(r * CHUNK + s_ + 1);
+                }
+                ra += Stage::kRecBytes;
+                ia += 4;
             }
-            ra += Stage::kRecBytes;
-            ia += 4;
+            if (__all_sync(kFull, T == 0.0f)) break;  // every pixel of the block is saturated
         }
-        if (__all_sync(kFull, T == 0.0f)) break;  // every pixel of the block is saturated
+        stage.drain();  // never leave with copies still in flight into this CTA's shared memory
     }
-    // never leave with bulk copies still in flight into this CTA's shared memory
-    for (int r = consumed; r < issued; ++r) stage.wait(r & 1, (uint32_t)((r >> 1) & 1));
     if (T != 0.0f) T_final = T;  // never terminated
 
     if (inside) {
@@ -140,7 +113,9 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
         const size_t pix = (size_t)py * p.W + px;
         T = T_final;
         p.final_T[pix] = T;
-        p.n_contrib[pix] = last_contributor;
+        // the reference's n_contrib: position of the last contributor in the TILE list + 1
+        p.n_contrib[pix] = last_k ? __ldg(list + (last_k - 1)) + 1u : 0u;
+        p.k_contrib[pix] = last_k;
 #pragma unroll
         for (int c = 0; c < 3; ++c) p.out_color[c * HW + pix] = acc[c] + T * p.bg[c];
         int base = 3;
@@ -173,20 +148,14 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     }
 }
 
-template <int CT4, int CHUNK>
-int launch_fwd_tc(const RenderParams& p, cudaStream_t stream, bool debug) {
-    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    const size_t smem = WarpStage<RS, CHUNK>::kSmemBytes;
-    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
-    render_fwd_kernel<CT4, CHUNK><<<(unsigned)blocks, 32, smem, stream>>>(p);
-    LSX_KERNEL_OK(stream, debug);
-    return 0;
-}
-
 template <int CT4>
 int launch_fwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
-    // rounds of 16 list entries keep a block's staging buffers at ~5 KB, so 32 blocks fit on an SM
-    return tune_chunk() == 32 ? launch_fwd_tc<CT4, 32>(p, stream, debug) : launch_fwd_tc<CT4, 16>(p, stream, debug);
+    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    const size_t smem = ListStage<RS>::kSmemBytes;  // two 16-record buffers: ~5 KB, so 32 blocks fit on an SM
+    const long long blocks = (long long)p.grid_x * p.grid_y * 8;
+    render_fwd_kernel<CT4><<<(unsigned)blocks, 32, smem, stream>>>(p);
+    LSX_KERNEL_OK(stream, debug);
+    return 0;
 }
 
 }  // namespace

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("LSX_B200_LIB", os.path.join(_PKG_DIR, "liblsx_b200.so
 
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_BLEND_CHANNELS = 40
 
 
@@ -65,6 +65,7 @@ class ScratchLayout(ctypes.Structure):
         ("record_stride", c_int32), ("geom_bytes", c_size_t),
         ("final_T", c_size_t), ("n_contrib", c_size_t), ("ranges", c_size_t), ("image_bytes", c_size_t),
         ("point_list", c_size_t), ("binning_bytes", c_size_t), ("masks", c_size_t),
+        ("blk_list", c_size_t), ("blk_cnt", c_size_t), ("k_contrib", c_size_t),
     ]
 
 

@@ -101,6 +101,9 @@ def parse_new_buffers(geom, binning, img, P, R, W, H, n_blend):
     if R > 0:
         out["point_list"] = _view(binning, lay.point_list, R, torch.int32)
         out["masks"] = _view(binning, lay.masks, R, torch.uint8)
+        out["blk_list"] = _view(binning, lay.blk_list, 8 * R, torch.int32).view(8, R)
+        out["blk_cnt"] = _view(binning, lay.blk_cnt, 8 * T, torch.int32).view(T, 8)
+        out["k_contrib"] = _view(img, lay.k_contrib, N, torch.int32)
         keys = torch.empty(R, dtype=torch.int64, device=geom.device)
         _lib.check(lib.lsx_debug_sorted_keys(P, W, H, R, n_blend, geom.data_ptr(), binning.data_ptr(), img.data_ptr(),
                                              keys.data_ptr(), torch.cuda.current_stream().cuda_stream), "debug keys")

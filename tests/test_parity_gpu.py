@@ -420,6 +420,25 @@ def test_footprint_masks_against_brute_force(s_med, aniso, opac_shift, scale_mod
     assert violations == 0, f"{violations} (block, entry) pairs would blend but are masked out"
     assert kept < total          # the masks do remove work on these scenes
     print(f"masks keep {kept / total:.1%} of the (block, entry) pairs")
+    # the compacted per-block lists the render kernels walk are exactly the set bits, in list order
+    pos_in_tile = torch.arange(R, device="cuda:0") - ranges[tile_of, 0]
+    for w in range(8):
+        bit = ((masks >> w) & 1).bool()
+        want_cnt = torch.zeros(ranges.shape[0], dtype=torch.long, device="cuda:0").index_add_(0, tile_of[bit], torch.ones_like(tile_of[bit]))
+        assert torch.equal(buf["blk_cnt"][:, w].long(), want_cnt)
+        # entries of tile t with the bit set, in order, live at blk_list[w, start_t : start_t + cnt_t]
+        rank = torch.cumsum(bit.long(), 0) - 1
+        first = torch.cumsum(want_cnt, 0) - want_cnt                    # set bits before each tile
+        slot = ranges[tile_of[bit], 0] + (rank[bit] - first[tile_of[bit]])
+        assert torch.equal(buf["blk_list"][w].long()[slot], pos_in_tile[bit])
+    # every pixel's k_contrib / n_contrib pair is consistent: n_contrib = list[k_contrib - 1] + 1
+    kc, nc = buf["k_contrib"].long().view(H, W), buf["n_contrib"].long().view(H, W)
+    ys, xs = torch.meshgrid(torch.arange(H, device="cuda:0"), torch.arange(W, device="cuda:0"), indexing="ij")
+    t_pix = (ys // 16) * gx + xs // 16
+    w_pix = ((ys % 16) // 4) * 2 + (xs % 16) // 8
+    has = kc > 0
+    got = buf["blk_list"].long()[w_pix[has], ranges[t_pix[has], 0] + kc[has] - 1] + 1
+    assert torch.equal(got, nc[has]) and bool((nc[~has] == 0).all())
 
 
 def test_too_many_channels_is_an_error():

@@ -1,5 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python tools/config_sweep.py > gpurun_out/r4n_config_sweep.jsonl 2> gpurun_out/r4n_config_sweep.err
-for c in C4 C2 C3; do timeout 300 python tools/loop_bench.py --config $c >> gpurun_out/r4n_loop_skeleton.jsonl 2>> gpurun_out/r4n_loop.err; done
-cat gpurun_out/r4n_config_sweep.jsonl gpurun_out/r4n_loop_skeleton.jsonl | cut -c1-400
+L=gpurun_out/r5a.log
+: > $L
+timeout 900 python -m pytest tests/test_parity_gpu.py -x -q 2>&1 | grep -v "^$" | tail -40 >> $L
+timeout 300 python tools/stage_times.py C3 C4 C5 >> $L 2>&1
+cat $L
