@@ -1,6 +1,6 @@
-// async_copy.cuh — mbarrier + 1-D bulk (TMA engine, cp.async.bulk -> SASS UBLKCP) helpers, sm_100a.
-// Used by the tile renderers to stage per-tile batches of packed Gaussian records into shared memory
-// while the previous batch is being blended.
+// async_copy.cuh — asynchronous global -> shared copy helpers (cp.async -> SASS LDGSTS / LDGDEPBAR / DEPBAR), sm_100a.
+// Used by the tile renderers to stage batches of packed Gaussian records into shared memory while the previous
+// batch is being blended.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -8,43 +8,6 @@
 namespace lsx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrive_count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrive_count) : "memory");
-}
-
-// make barrier initialisation visible to the async (TMA) proxy
-__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase_parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LSX_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LSX_DONE_%=;\n"
-        "bra LSX_WAIT_%=;\n"
-        "LSX_DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase_parity)
-        : "memory");
-}
-
-// global -> shared bulk copy; bytes must be a multiple of 16, both addresses 16-B aligned.
-__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // ---- per-thread asynchronous 16-B copies (cp.async -> SASS LDGSTS): unlike the bulk copy, whose operands live in
 // uniform registers (one elected lane per copy), every lane supplies its own source / destination.

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
                                                               uint32_t* __restrict__ blk_list, size_t list_stride,
                                                               uint32_t* __restrict__ blk_cnt) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ uint32_t s_cnt[8][8];  // [warp][block]
+    __shared__ uint32_t s_cnt[2][8][8];  // [chunk parity][warp][block]: double-buffered, one barrier per chunk
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
     const uint32_t n = r.y - r.x;
@@ -104,30 +104,51 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     uint32_t run = 0;  // lanes 0..7 (of every warp): entries of block `lane` emitted by earlier chunks
-    for (uint32_t base = 0; base < n; base += 256) {
+    // software pipeline over the 256-entry chunks: the record head of chunk c + 1 and the Gaussian index of chunk c + 2
+    // are in flight while chunk c is classified and compacted (the two loads are dependent: index -> record)
+    auto load_id = [&](uint32_t i) -> uint32_t { return i < n ? __ldg(point_list + r.x + i) : 0u; };
+    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 h1 = make_float2(0.f, 0.f);
+    {
+        const uint32_t id0 = load_id(threadIdx.x);
+        if (threadIdx.x < n) {
+            const float* rec = records + (size_t)id0 * rec_stride;
+            h0 = __ldg(reinterpret_cast<const float4*>(rec));
+            h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
+        }
+    }
+    uint32_t id_next = load_id(256u + threadIdx.x);
+    unsigned parity = 0;
+    for (uint32_t base = 0; base < n; base += 256, parity ^= 1u) {
         const uint32_t i = base + threadIdx.x;
+        float4 nh0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float2 nh1 = make_float2(0.f, 0.f);
+        if (i + 256u < n) {
+            const float* rec = records + (size_t)id_next * rec_stride;
+            nh0 = __ldg(reinterpret_cast<const float4*>(rec));
+            nh1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
+        }
+        id_next = load_id(i + 512u);
         unsigned m = 0u;
         if (i < n) {
-            const float* rec = records + (size_t)point_list[r.x + i] * rec_stride;
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(rec));
-            const float2 h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
             m = footprint_mask(h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, tx0, ty0);
             masks[r.x + i] = (uint8_t)m;
         }
+        unsigned bal[8];
         uint32_t wtotal = 0;
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-            const uint32_t t = __popc(__ballot_sync(kFull, (m >> w) & 1u));
-            if (lane == (unsigned)w) wtotal = t;
+            bal[w] = __ballot_sync(kFull, (m >> w) & 1u);
+            if (lane == (unsigned)w) wtotal = __popc(bal[w]);
         }
-        if (lane < 8) s_cnt[warp][lane] = wtotal;
+        if (lane < 8) s_cnt[parity][warp][lane] = wtotal;
         __syncthreads();
         uint32_t wbase = 0;
         if (lane < 8) {
             uint32_t before = 0, total = 0;
 #pragma unroll
             for (int w2 = 0; w2 < 8; ++w2) {
-                const uint32_t c = s_cnt[w2][lane];
+                const uint32_t c = s_cnt[parity][w2][lane];
                 before += ((unsigned)w2 < warp) ? c : 0u;
                 total += c;
             }
@@ -136,12 +157,11 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
         }
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
-            const bool set = ((m >> w) & 1u) != 0u;
-            const unsigned bal = __ballot_sync(kFull, set);
             const uint32_t b0 = __shfl_sync(kFull, wbase, w);
-            if (set) blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal & lt)] = i;
+            if ((m >> w) & 1u) blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal[w] & lt)] = i;
         }
-        __syncthreads();  // s_cnt is rewritten by the next chunk
+        h0 = nh0;
+        h1 = nh1;
     }
     if (warp == 0 && lane < 8) blk_cnt[8 * tile + lane] = run;
 }

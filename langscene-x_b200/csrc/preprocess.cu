@@ -12,7 +12,7 @@
 //       - emits the 32-bit depth sort key (0xFFFFFFFF for culled splats) for the depth-major presort,
 //       - packs every attribute the tile renderers need into ONE sector-aligned record per Gaussian
 //         ({xy, conic, opacity} + all blended channels), so that the per-tile staging is a single
-//         contiguous bulk copy per list entry instead of 5 scattered gathers.
+//         contiguous copy per list entry instead of 5 scattered gathers.
 //   * the backward kernel fuses the reference's computeCov2DCUDA + preprocessCUDA launches and writes
 //     every gradient row exactly once (zeros for culled splats), which removes ~400 MB of separate
 //     zero-fill traffic at 1M Gaussians.
