@@ -72,21 +72,35 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
     }
 }
 
+// four consecutive keys per thread (one 16-B load + the preceding key)
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys,
                                                           uint2* __restrict__ ranges) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const uint32_t t = keys[i];
-    if (i == 0) {
-        ranges[t].x = 0;
+    const long long base = 4ll * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+    if (base >= R) return;
+    uint32_t k[4];
+    if (base + 3 < R) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(keys + base));
+        k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
     } else {
-        const uint32_t prev = keys[i - 1];
-        if (prev != t) {
-            ranges[prev].y = i;
-            ranges[t].x = i;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k[j] = (base + j < R) ? keys[base + j] : 0u;
+    }
+    uint32_t prev = base > 0 ? __ldg(keys + base - 1) : 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long i = base + j;
+        if (i < R) {
+            const uint32_t t = k[j];
+            if (i == 0) {
+                ranges[t].x = 0;
+            } else if (prev != t) {
+                ranges[prev].y = (uint32_t)i;
+                ranges[t].x = (uint32_t)i;
+            }
+            if (i == R - 1) ranges[t].y = (uint32_t)R;
+            prev = t;
         }
     }
-    if (i == R - 1) ranges[t].y = R;
 }
 
 __global__ void __launch_bounds__(256) debug_keys_kernel(int num_tiles, const uint2* __restrict__ ranges,
@@ -116,7 +130,7 @@ int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, i
                        bool debug) {
     LSX_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
     if (R <= 0) return 0;
-    tile_ranges_kernel<<<ceil_div(R, 256), 256, 0, stream>>>(R, sorted_tile_keys, ranges);
+    tile_ranges_kernel<<<ceil_div(ceil_div(R, 4), 256), 256, 0, stream>>>(R, sorted_tile_keys, ranges);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

@@ -117,4 +117,53 @@ __device__ __forceinline__ void slab_store(float* __restrict__ g, const float* _
     }
 }
 
+// global -> global: dst (rows x rowf, contiguous) = columns [col0, col0 + rowf) of src rows of `src_stride` floats
+// (accumulate: dst += ...).  Stores are coalesced 16-B accesses in thread order; the gathers walk contiguous runs of a
+// row, so the sectors one load instruction touches are used up by the next three.
+template <int NT>
+__device__ __forceinline__ void slab_copy_columns(float* __restrict__ dst, const float* __restrict__ src, int rows, int rowf,
+                                                  int src_stride, int col0, bool accumulate) {
+    const int total = rows * rowf;
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && rowf >= 4) {
+        const int n4 = total >> 2;
+        const int step = NT * 4;
+        const int dq = step / rowf, dr = step - dq * rowf;
+        int e = tid * 4;
+        int r = e / rowf, c = e - r * rowf;
+        for (int i = tid; i < n4; i += NT) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (accumulate) o = reinterpret_cast<const float4*>(dst)[i];
+            float vv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int ck = c + k, rk = r;
+                if (ck >= rowf) {
+                    ck -= rowf;
+                    ++rk;
+                }
+                vv[k] = __ldg(src + (size_t)rk * src_stride + col0 + ck);
+            }
+            reinterpret_cast<float4*>(dst)[i] = make_float4(vv[0] + o.x, vv[1] + o.y, vv[2] + o.z, vv[3] + o.w);
+            r += dq;
+            c += dr;
+            if (c >= rowf) {
+                c -= rowf;
+                ++r;
+            }
+        }
+        for (int e2 = (n4 << 2) + tid; e2 < total; e2 += NT) {
+            const int r2 = e2 / rowf;
+            const float v = __ldg(src + (size_t)r2 * src_stride + col0 + (e2 - r2 * rowf));
+            dst[e2] = accumulate ? dst[e2] + v : v;
+        }
+    } else {
+        for (int e2 = tid; e2 < total; e2 += NT) {
+            const int r2 = e2 / rowf;
+            const float v = __ldg(src + (size_t)r2 * src_stride + col0 + (e2 - r2 * rowf));
+            dst[e2] = accumulate ? dst[e2] + v : v;
+        }
+    }
+}
+
 }  // namespace lsx

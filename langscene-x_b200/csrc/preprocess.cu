@@ -311,10 +311,9 @@ __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const Pr
 constexpr int kPreBwdThreads = LSX_PRE_BWD_THREADS;
 
 __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, float* __restrict__ sh_row,
-                                                   const float* __restrict__ grec) {
+                                                   const float (&grec)[3], const float (&ggeo)[8]) {
     const int n_sh = p.M * 3;
     float* g_sh = p.dL_dsh ? sh_row : nullptr;
-    const float* ggeo = grec + p.n_channels_pad;
     p.dL_dmean2D[3 * idx + 0] = ggeo[0];
     p.dL_dmean2D[3 * idx + 1] = ggeo[1];
     p.dL_dmean2D[3 * idx + 2] = 0.f;
@@ -608,32 +607,44 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
 __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const PreprocessBwdParams p) {
     extern __shared__ __align__(16) float s_pre[];
     const int n_sh = p.M * 3;
-    const int sh_row = padded_row(n_sh), rec_row = padded_row(p.grad_stride);
+    const int sh_row = padded_row(n_sh);
     float* s_sh = s_pre;
-    float* s_rec = s_pre + (p.shs ? kPreBwdThreads * sh_row : 0);
     const int b0 = blockIdx.x * kPreBwdThreads;
     const int rows = min(kPreBwdThreads, p.P - b0);
-    if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
-    slab_load<kPreBwdThreads, kBwdSlabDepth>(s_rec, p.grad_records + (size_t)b0 * p.grad_stride, rows, p.grad_stride, rec_row);
-    __syncthreads();
-    if ((int)threadIdx.x < rows)
-        preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, s_rec + threadIdx.x * rec_row);
-    __syncthreads();
     const bool acc = p.accumulate != 0;
-    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, acc);
-    slab_store<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, s_rec, rows, 3, rec_row, 0, acc);
+    const float* rec0 = p.grad_records + (size_t)b0 * p.grad_stride;
+    // the thread's own colour gradient and 8 geometry terms, straight from its record (16-B aligned: both offsets are
+    // multiples of 4 floats)
+    float gcol[3] = {0.f, 0.f, 0.f}, ggeo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if ((int)threadIdx.x < rows) {
+        const float* rec = rec0 + (size_t)threadIdx.x * p.grad_stride;
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(rec));
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(rec + p.n_channels_pad));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(rec + p.n_channels_pad + 4));
+        gcol[0] = c4.x; gcol[1] = c4.y; gcol[2] = c4.z;
+        ggeo[0] = g0.x; ggeo[1] = g0.y; ggeo[2] = g0.z; ggeo[3] = g0.w;
+        ggeo[4] = g1.x; ggeo[5] = g1.y; ggeo[6] = g1.z; ggeo[7] = g1.w;
+    }
+    if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
+    // The blended channels' gradients leave the records unchanged: copied record columns -> the reference's tensors with
+    // coalesced 16-B stores, no shared-memory tile (the tile cost 19 KB per block and with it 3 of 8 resident blocks).
+    slab_copy_columns<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, rec0, rows, 3, p.grad_stride, 0, acc);
     int c = 3;
     if (p.include_feature) {
-        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, s_rec, rows, p.F, rec_row, c, acc);
+        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, rec0, rows, p.F, p.grad_stride, c, acc);
         c += p.F;
-        slab_store<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, s_rec, rows, p.Fi, rec_row, c, acc);
+        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, rec0, rows, p.Fi, p.grad_stride, c, acc);
         c += p.Fi;
     }
     if (p.render_geo) {
-        slab_store<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, s_rec, rows, 5, rec_row, c, acc);
+        slab_copy_columns<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, rec0, rows, 5, p.grad_stride, c, acc);
     } else if (!acc) {
         for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
     }
+    __syncthreads();
+    if ((int)threadIdx.x < rows) preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, gcol, ggeo);
+    __syncthreads();
+    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, acc);
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -678,7 +689,7 @@ int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, boo
 
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
-    const size_t smem = (size_t)kPreBwdThreads * ((p.shs ? padded_row(p.M * 3) : 0) + padded_row(p.grad_stride)) * sizeof(float);
+    const size_t smem = (size_t)kPreBwdThreads * (p.shs ? padded_row(p.M * 3) : 0) * sizeof(float);
     LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel), smem, 1));
     preprocess_bwd_kernel<<<ceil_div(p.P, kPreBwdThreads), kPreBwdThreads, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
