@@ -129,10 +129,18 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
     h[threadIdx.x] = 0;
     __syncthreads();
     const int base = blockIdx.x * kTile;
+    // all 16 keys of the thread are fetched before the first shared-memory atomic (interleaved, every atomic waited for
+    // its own load: the kernel was a chain of 16 exposed global-load latencies)
+    uint32_t k[kItems];
 #pragma unroll
     for (int i = 0; i < kItems; ++i) {
         const int idx = base + i * kThreads + threadIdx.x;
-        if (idx < n) atomicAdd(&h[(keys[idx] >> shift) & mask], 1u);
+        k[i] = idx < n ? __ldg(keys + idx) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < kItems; ++i) {
+        const int idx = base + i * kThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[(k[i] >> shift) & mask], 1u);
     }
     __syncthreads();
     const uint32_t c = h[threadIdx.x];
