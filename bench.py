@@ -36,10 +36,10 @@ import torch.distributed as dist  # noqa: E402
 
 METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r5c_ncu_kernels.md: the kernels as shipped at the end of round 1)
-NCU_TRAFFIC = {"render_bwd": 650083328, "render_fwd": 448444160}
+# (profiles/r5m_ncu_render_kernels.md: the render kernels as shipped at the end of round 1)
+NCU_TRAFFIC = {"render_bwd": 651566080, "render_fwd": 448174848}
 # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture: what actually bounds these kernels
-NCU_ISSUE_BUSY_PCT = {"render_bwd": 75.5, "render_fwd": 86.8}
+NCU_ISSUE_BUSY_PCT = {"render_bwd": 74.7, "render_fwd": 86.8}
 
 
 def load_peaks():

@@ -518,6 +518,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     bp.grad_records = gm.grad_records; bp.grad_stride = gs; bp.n_channels_pad = round_up4(nch);
     bp.F = F; bp.Fi = Fi; bp.include_feature = a->include_feature; bp.render_geo = a->render_geo;
     bp.accumulate = a->accumulate_param_grads;
+    bp.geo_scale_x = 0.5f * (float)W; bp.geo_scale_y = 0.5f * (float)H;
     bp.dL_dmean2D = a->dL_dmeans2D; bp.dL_dmean2D_abs = a->dL_dmeans2D_abs; bp.dL_dconic = a->dL_dconic;
     bp.dL_dopacity = a->dL_dopacity; bp.dL_dcolor = a->dL_dcolors;
     bp.dL_dlanguage_feature = a->dL_dlanguage_feature;

@@ -60,6 +60,9 @@ struct PreprocessBwdParams {
     int n_channels_pad;  // round_up4(blended channels) = offset of the geometry terms inside a record
     int F, Fi, include_feature, render_geo;
     int accumulate;  // parameter gradients: out += value (multi-view accumulation) instead of out = value
+    // the tile pass leaves the constant factors of the geometry terms (0.5 W / 0.5 H of the mean2D
+    // terms, -0.5 of the conic terms) to this kernel, which applies them once per Gaussian instead of once per visit
+    float geo_scale_x, geo_scale_y;
     // per-tensor outputs in the reference's layouts (every row written; zeros for culled splats)
     float* dL_dmean2D;      // (P,3)
     float* dL_dmean2D_abs;  // (P,3)

@@ -624,6 +624,8 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
         gcol[0] = c4.x; gcol[1] = c4.y; gcol[2] = c4.z;
         ggeo[0] = g0.x; ggeo[1] = g0.y; ggeo[2] = g0.z; ggeo[3] = g0.w;
         ggeo[4] = g1.x; ggeo[5] = g1.y; ggeo[6] = g1.z; ggeo[7] = g1.w;
+        ggeo[0] *= p.geo_scale_x; ggeo[1] *= p.geo_scale_y; ggeo[2] *= p.geo_scale_x; ggeo[3] *= p.geo_scale_y;
+        ggeo[4] *= -0.5f; ggeo[5] *= -0.5f; ggeo[6] *= -0.5f;
     }
     if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
     // The blended channels' gradients leave the records unchanged: copied record columns -> the reference's tensors with
