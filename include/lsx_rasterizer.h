@@ -43,7 +43,7 @@ extern "C" {
 #define LSX_API
 #endif
 
-#define LSX_ABI_VERSION 4
+#define LSX_ABI_VERSION 5
 #define LSX_MAX_BLEND_CHANNELS 40 /* 3 + F + Fi + 5 must not exceed this */
 
 /* scratch allocation callback: must return a device pointer to at least `bytes` bytes, aligned to
@@ -145,12 +145,23 @@ typedef struct lsx_backward_args {
     float* dL_dall_map;      /* P*5 */
     void* stream;
     /* Multi-view gradient accumulation (no reference counterpart: the reference returns fresh tensors and lets autograd add
-     * them).  When non-zero, the PARAMETER gradients — dL_dmeans3D, dL_dsh, dL_dopacity, dL_dscales, dL_drotations,
-     * dL_dcolors, dL_dlanguage_feature(_instance), dL_dall_map, dL_dcov3D — are added to the buffers' current contents
-     * (which must then be initialised) instead of overwriting them; the per-view screen-space outputs dL_dmeans2D,
-     * dL_dmeans2D_abs and dL_dconic are always overwritten. */
+     * them).  Bit mask (LSX_ACC_*, below) of the PARAMETER gradients that are ADDED to their buffer's current contents
+     * (which must then be initialised) instead of overwriting it; 0 = overwrite everything.  The per-view screen-space
+     * outputs dL_dmeans2D, dL_dmeans2D_abs and dL_dconic are always overwritten.  (ABI v5: was a boolean for all groups.) */
     int32_t accumulate_param_grads;
 } lsx_backward_args;
+
+#define LSX_ACC_MEANS3D 0x001
+#define LSX_ACC_SH 0x002
+#define LSX_ACC_OPACITY 0x004
+#define LSX_ACC_SCALES 0x008
+#define LSX_ACC_ROTATIONS 0x010
+#define LSX_ACC_COLORS 0x020
+#define LSX_ACC_LANG 0x040
+#define LSX_ACC_INST 0x080
+#define LSX_ACC_ALL_MAP 0x100
+#define LSX_ACC_COV3D 0x200
+#define LSX_ACC_ALL 0x3ff
 
 LSX_API int lsx_rasterize_backward(const lsx_backward_args* args);
 
@@ -208,6 +219,14 @@ LSX_API int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const
                                        const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
                                        const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
                                        float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw, void* stream);
+/* Same, with `accumulate_mask`: bit 0 dL_dxyz, bit 1 dL_dscaling_raw, bit 2 dL_drotation_raw, bit 3 dL_dopacity_raw are ADDED
+ * to the buffers' contents (the views of a multi-view gradient arena) instead of written. */
+LSX_API int lsx_gaussian_head_backward_acc(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
+                                           const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                           const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
+                                           const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
+                                           float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw,
+                                           int32_t accumulate_mask, void* stream);
 
 /* Adam step over flat fp32 arenas (parameters, gradients, both moments share one layout of n elements).  Replaces
  * torch.optim.Adam(groups, lr=0.0, eps=1e-15).step() of the reference (field_construction/scene/gaussian_model.py:313-328,
@@ -401,6 +420,15 @@ LSX_API int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R,
 LSX_API int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,
                           const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
                           uint64_t* keys_out, void* stream);
+
+/* Workload counters of one rendered view, counted on the device from the scratch of a forward call (S, B, R
+ * accompany every number).  stats_out: DEVICE array of 8 uint64, written as
+ *   [0] S   sum of n_contrib = (pixel, entry) tests per pass of the reference's render loops (forward.cu:335-407)
+ *   [1] B   (pixel, entry) pairs actually blended (alpha >= 1/255, power <= 0, at or before the pixel's last contributor)
+ *   [2] V   (8x4 block, entry) visits of this library's backward pass      [3] Vb  visits in which some pixel blends
+ *   [4] L   total length of the per-block compacted lists                  [5..7] reserved (0) */
+LSX_API int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
+                     const char* binning_buffer, const char* image_buffer, uint64_t* stats_out, void* stream);
 
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */
 LSX_API uint64_t lsx_kernel_launch_count(void);

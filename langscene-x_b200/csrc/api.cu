@@ -567,4 +567,29 @@ int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_
     return launch_debug_keys(tiles, im.ranges, bn.point_list, gm.depths, keys_out, static_cast<cudaStream_t>(stream));
 }
 
+int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
+                     const char* binning_buffer, const char* image_buffer, uint64_t* stats_out, void* stream) {
+    if (P < 0 || W <= 0 || H <= 0 || R < 0 || !stats_out || n_blend_channels < 3 || n_blend_channels > LSX_MAX_BLEND_CHANNELS ||
+        (P > 0 && (!geom_buffer || !image_buffer)) || (R > 0 && !binning_buffer)) {
+        set_error("lsx_render_stats: bad arguments");
+        return -1;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (P == 0 || R == 0) {
+        LSX_CUDA_OK(cudaMemsetAsync(stats_out, 0, 8 * sizeof(uint64_t), st));
+        return 0;
+    }
+    const int rs = record_stride(n_blend_channels);
+    GeomScratch gm = carve_geom(const_cast<char*>(geom_buffer), P, rs);
+    ImageScratch im = carve_image(const_cast<char*>(image_buffer), W, H, nullptr);
+    const uint32_t grid_x = (uint32_t)ceil_div(W, TILE_X), grid_y = (uint32_t)ceil_div(H, TILE_Y);
+    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), R, (int)(grid_x * grid_y), nullptr);
+    RenderParams rp{};
+    rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.n_channels = n_blend_channels; rp.rec_stride = rs;
+    rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.records = gm.records;
+    rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
+    rp.n_contrib = im.n_contrib;
+    return launch_render_stats(rp, reinterpret_cast<unsigned long long*>(stats_out), st);
+}
+
 }  // extern "C"

@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
     const float* __restrict__ rotation_raw, const float* __restrict__ opacity_raw, const float* __restrict__ g_scales,
     const float* __restrict__ g_rotations, const float* __restrict__ g_opacity, const float* __restrict__ g_all_map,
     const float* __restrict__ g_means3D, float* __restrict__ g_xyz, float* __restrict__ g_scaling_raw,
-    float* __restrict__ g_rotation_raw, float* __restrict__ g_opacity_raw) {
+    float* __restrict__ g_rotation_raw, float* __restrict__ g_opacity_raw, const unsigned acc) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
+    // acc: bit 0 xyz, 1 scaling, 2 rotation, 3 opacity — add to the buffer instead of writing it
+    auto put = [acc](float* dst, const float v, const unsigned bit) { *dst = (acc & bit) ? *dst + v : v; };
     const HeadCam c = load_cam(view, campos);
     const float x[3] = {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]};
     const float s[3] = {scaling_raw[3 * i], scaling_raw[3 * i + 1], scaling_raw[3 * i + 2]};
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
 
     // activations
 #pragma unroll
-    for (int a = 0; a < 3; ++a) g_scaling_raw[3 * i + a] = (g_scales ? g_scales[3 * i + a] : 0.f) * f.sc[a];
-    g_opacity_raw[i] = (g_opacity ? g_opacity[i] : 0.f) * f.sig * (1.0f - f.sig);
+    for (int a = 0; a < 3; ++a) put(g_scaling_raw + 3 * i + a, (g_scales ? g_scales[3 * i + a] : 0.f) * f.sc[a], 2u);
+    put(g_opacity_raw + i, (g_opacity ? g_opacity[i] : 0.f) * f.sig * (1.0f - f.sig), 8u);
 
     // all_map -> local normal, camera-space point
     float gam[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
     for (int r = 0; r < 3; ++r) {
         g_col[r] = f.flip * (g_nl[0] * c.v[4 * r] + g_nl[1] * c.v[4 * r + 1] + g_nl[2] * c.v[4 * r + 2]);
         const float gx = g_pc[0] * c.v[4 * r] + g_pc[1] * c.v[4 * r + 1] + g_pc[2] * c.v[4 * r + 2];
-        g_xyz[3 * i + r] = gx + (g_means3D ? g_means3D[3 * i + r] : 0.f);
+        put(g_xyz + 3 * i + r, gx + (g_means3D ? g_means3D[3 * i + r] : 0.f), 1u);
     }
     // column idx of R(q): entry e = const + s2 * fe(q);  d e / d q_m = s2 * d fe / d q_m - s2^2 * q_m * fe   (|q| = 1 here,
     // but pytorch3d's two_s = 2 / |q|^2 is differentiated too)
@@ -173,6 +175,10 @@ __global__ void __launch_bounds__(256) gaussian_head_bwd_kernel(
     } else {
         out = make_float4(gq[0] / f.nq, gq[1] / f.nq, gq[2] / f.nq, gq[3] / f.nq);  // q = q_raw / eps
     }
+    if (acc & 4u) {
+        const float4 o = reinterpret_cast<const float4*>(g_rotation_raw)[i];
+        out = make_float4(out.x + o.x, out.y + o.y, out.z + o.z, out.w + o.w);
+    }
     reinterpret_cast<float4*>(g_rotation_raw)[i] = out;
 }
 
@@ -197,11 +203,12 @@ extern "C" int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix, con
     return 0;
 }
 
-extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
-                                          const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
-                                          const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
-                                          const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
-                                          float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw, void* stream_) {
+extern "C" int lsx_gaussian_head_backward_acc(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
+                                              const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                              const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
+                                              const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
+                                              float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw,
+                                              int32_t accumulate_mask, void* stream_) {
     if (P < 0 || !viewmatrix || !campos ||
         (P > 0 && (!xyz || !scaling_raw || !rotation_raw || !opacity_raw || !dL_dxyz || !dL_dscaling_raw || !dL_drotation_raw ||
                    !dL_dopacity_raw))) {
@@ -213,7 +220,17 @@ extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, co
     gaussian_head_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw,
                                                                    opacity_raw, dL_dscales, dL_drotations,
                                                                    dL_dopacity, dL_dall_map, dL_dmeans3D, dL_dxyz, dL_dscaling_raw,
-                                                                   dL_drotation_raw, dL_dopacity_raw);
+                                                                   dL_drotation_raw, dL_dopacity_raw, (unsigned)accumulate_mask);
     LSX_KERNEL_OK(stream, false);
     return 0;
+}
+
+extern "C" int lsx_gaussian_head_backward(int32_t P, const float* viewmatrix, const float* campos, const float* xyz,
+                                          const float* scaling_raw, const float* rotation_raw, const float* opacity_raw,
+                                          const float* dL_dscales, const float* dL_drotations, const float* dL_dopacity,
+                                          const float* dL_dall_map, const float* dL_dmeans3D, float* dL_dxyz,
+                                          float* dL_dscaling_raw, float* dL_drotation_raw, float* dL_dopacity_raw, void* stream_) {
+    return lsx_gaussian_head_backward_acc(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw, opacity_raw, dL_dscales,
+                                          dL_drotations, dL_dopacity, dL_dall_map, dL_dmeans3D, dL_dxyz, dL_dscaling_raw,
+                                          dL_drotation_raw, dL_dopacity_raw, 0, stream_);
 }

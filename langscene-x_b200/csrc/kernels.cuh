@@ -1,6 +1,7 @@
 // kernels.cuh — parameter blocks and launcher prototypes shared by the .cu files of liblsx_b200.so
 #pragma once
 #include <cstdio>
+#include "../../include/lsx_rasterizer.h"
 #include "common.cuh"
 
 namespace lsx {
@@ -59,7 +60,7 @@ struct PreprocessBwdParams {
     int grad_stride;  // floats per record
     int n_channels_pad;  // round_up4(blended channels) = offset of the geometry terms inside a record
     int F, Fi, include_feature, render_geo;
-    int accumulate;  // parameter gradients: out += value (multi-view accumulation) instead of out = value
+    int accumulate;  // LSX_ACC_* bit mask: parameter gradients with out += value (multi-view accumulation) instead of out = value
     // the tile pass leaves the constant factors of the geometry terms (0.5 W / 0.5 H of the mean2D
     // terms, -0.5 of the conic terms) to this kernel, which applies them once per Gaussian instead of once per visit
     float geo_scale_x, geo_scale_y;
@@ -156,6 +157,8 @@ struct RenderParams {
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream, bool debug);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream, bool debug);
+// stats.cu: S, B, V, Vb, L of a rendered view (needs ranges, point_list, blk_list/blk_cnt, records, n_contrib, k_contrib)
+int launch_render_stats(const RenderParams& p, unsigned long long* out8, cudaStream_t stream);
 
 // ---- KNN (knn.cu) -------------------------------------------------------------------------------
 size_t knn_temp_bytes(int P);

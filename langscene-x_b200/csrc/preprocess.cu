@@ -321,21 +321,26 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
     p.dL_dmean2D_abs[3 * idx + 1] = ggeo[3];
     p.dL_dmean2D_abs[3 * idx + 2] = 0.f;
     reinterpret_cast<float4*>(p.dL_dconic)[idx] = make_float4(ggeo[4], ggeo[5], 0.f, ggeo[6]);
-    const bool acc = p.accumulate != 0;
-    auto put = [acc](float* dst, const float v) { *dst = acc ? *dst + v : v; };
-    put(p.dL_dopacity + idx, ggeo[7]);
+    // p.accumulate: bit mask of the outputs that are ADDED to (multi-view accumulation) instead of written
+    const unsigned am = (unsigned)p.accumulate;
+    auto put = [am](float* dst, const float v, const unsigned bit) { *dst = (am & bit) ? *dst + v : v; };
+    put(p.dL_dopacity + idx, ggeo[7], LSX_ACC_OPACITY);
 
     if (!(p.radii[idx] > 0)) {
         // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
-        if (!acc) {
+        if (!(am & LSX_ACC_MEANS3D)) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
+        }
+        if (!(am & LSX_ACC_COV3D)) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = 0.f;
+        }
+        if (!(am & LSX_ACC_SCALES)) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
-            reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        if (!(am & LSX_ACC_ROTATIONS)) reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g_sh)
             for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
         return;
@@ -386,7 +391,7 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < 6; ++i) g_cov[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) put(p.dL_dcov3D + 6 * idx + i, g_cov[i]);
+    for (int i = 0; i < 6; ++i) put(p.dL_dcov3D + 6 * idx + i, g_cov[i], LSX_ACC_COV3D);
 
     // gradient w.r.t. the upper 2x3 block of T
     float tv0[3], tv1[3];  // (row of T) . V columns
@@ -527,9 +532,9 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
     }
 
-    put(p.dL_dmeans3D + 3 * idx + 0, g_mean.x);
-    put(p.dL_dmeans3D + 3 * idx + 1, g_mean.y);
-    put(p.dL_dmeans3D + 3 * idx + 2, g_mean.z);
+    put(p.dL_dmeans3D + 3 * idx + 0, g_mean.x, LSX_ACC_MEANS3D);
+    put(p.dL_dmeans3D + 3 * idx + 1, g_mean.y, LSX_ACC_MEANS3D);
+    put(p.dL_dmeans3D + 3 * idx + 2, g_mean.z, LSX_ACC_MEANS3D);
 
     // ---- part 4: world covariance -> scale / rotation (backward.cu:278-341) ------------------------
     if (p.scales != nullptr) {
@@ -571,9 +576,12 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         const Mat3 Rt = mat3_transpose(R);
         Mat3 gMt = mat3_transpose(gM);
 
-        put(p.dL_dscales + 3 * idx + 0, Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2]);
-        put(p.dL_dscales + 3 * idx + 1, Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2]);
-        put(p.dL_dscales + 3 * idx + 2, Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2]);
+        put(p.dL_dscales + 3 * idx + 0, Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2],
+            LSX_ACC_SCALES);
+        put(p.dL_dscales + 3 * idx + 1, Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2],
+            LSX_ACC_SCALES);
+        put(p.dL_dscales + 3 * idx + 2, Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2],
+            LSX_ACC_SCALES);
 
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
@@ -589,15 +597,17 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
                4 * y * (gMt.m[2][2] + gMt.m[0][0]);
         gq.w = 2 * r * (gMt.m[0][1] - gMt.m[1][0]) + 2 * x * (gMt.m[2][0] + gMt.m[0][2]) + 2 * y * (gMt.m[1][2] + gMt.m[2][1]) -
                4 * z * (gMt.m[1][1] + gMt.m[0][0]);
-        if (acc) {
+        if (am & LSX_ACC_ROTATIONS) {
             const float4 o = reinterpret_cast<const float4*>(p.dL_drotations)[idx];
             gq = make_float4(gq.x + o.x, gq.y + o.y, gq.z + o.z, gq.w + o.w);
         }
         reinterpret_cast<float4*>(p.dL_drotations)[idx] = gq;  // w.r.t. the raw (un-normalised) quaternion
-    } else if (!acc) {
+    } else {
+        if (!(am & LSX_ACC_SCALES)) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
-        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
+        }
+        if (!(am & LSX_ACC_ROTATIONS)) reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -611,7 +621,7 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
     float* s_sh = s_pre;
     const int b0 = blockIdx.x * kPreBwdThreads;
     const int rows = min(kPreBwdThreads, p.P - b0);
-    const bool acc = p.accumulate != 0;
+    const unsigned am = (unsigned)p.accumulate;
     const float* rec0 = p.grad_records + (size_t)b0 * p.grad_stride;
     // the thread's own colour gradient and 8 geometry terms, straight from its record (16-B aligned: both offsets are
     // multiples of 4 floats)
@@ -630,23 +640,25 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
     if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
     // The blended channels' gradients leave the records unchanged: copied record columns -> the reference's tensors with
     // coalesced 16-B stores, no shared-memory tile (the tile cost 19 KB per block and with it 3 of 8 resident blocks).
-    slab_copy_columns<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, rec0, rows, 3, p.grad_stride, 0, acc);
+    slab_copy_columns<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, rec0, rows, 3, p.grad_stride, 0, (am & LSX_ACC_COLORS) != 0);
     int c = 3;
     if (p.include_feature) {
-        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, rec0, rows, p.F, p.grad_stride, c, acc);
+        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, rec0, rows, p.F, p.grad_stride, c,
+                                          (am & LSX_ACC_LANG) != 0);
         c += p.F;
-        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, rec0, rows, p.Fi, p.grad_stride, c, acc);
+        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, rec0, rows, p.Fi, p.grad_stride, c,
+                                          (am & LSX_ACC_INST) != 0);
         c += p.Fi;
     }
     if (p.render_geo) {
-        slab_copy_columns<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, rec0, rows, 5, p.grad_stride, c, acc);
-    } else if (!acc) {
+        slab_copy_columns<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, rec0, rows, 5, p.grad_stride, c, (am & LSX_ACC_ALL_MAP) != 0);
+    } else if (!(am & LSX_ACC_ALL_MAP)) {
         for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
     }
     __syncthreads();
     if ((int)threadIdx.x < rows) preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, gcol, ggeo);
     __syncthreads();
-    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, acc);
+    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, (am & LSX_ACC_SH) != 0);
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,

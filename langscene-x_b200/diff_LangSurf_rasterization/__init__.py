@@ -12,7 +12,11 @@ Differences (all behind the same outputs):
   * the language-feature width is taken from the tensor at run time (the reference bakes 3 into config.h);
   * `debug=True` works (the reference's debug branch unpacks the wrong tuple arity, :103): every stage is
     synchronised and checked, and on failure the arguments are dumped to snapshot_fw.dump / snapshot_bw.dump;
-  * work is enqueued on torch's current stream (the reference uses the legacy default stream).
+  * work is enqueued on torch's current stream (the reference uses the legacy default stream);
+  * multi-view extension (keyword-only, absent in the reference): `GaussianRasterizer(settings, grad_buffers=, accumulate=)`
+    lets the backward kernel write / add the per-Gaussian parameter gradients straight into caller-owned buffers (e.g. the
+    views of lsx_b200.multiview.GradArena); autograd then receives None for those inputs.  Use it when the rasterizer's
+    inputs ARE the leaves (no wrapper in between), as in a view-sharded gradient accumulation.
 """
 from typing import NamedTuple
 
@@ -59,8 +63,9 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, means2D_abs, sh, colors_precomp, language_feature_precomp,
                 language_feature_instance_precomp, opacities, scales, rotations, cov3Ds_precomp, all_maps,
-                raster_settings):
+                raster_settings, grad_sink=None):
         s = raster_settings
+        ctx.grad_sink = grad_sink
         native_args = (
             s.bg, means3D, colors_precomp, language_feature_precomp, language_feature_instance_precomp, opacities,
             scales, rotations, s.scale_modifier, cov3Ds_precomp, all_maps, s.viewmatrix, s.projmatrix,
@@ -95,35 +100,55 @@ class _RasterizeGaussians(torch.autograd.Function):
         (grad_means2D, grad_means2D_abs, grad_colors_precomp, grad_language_feature_precomp,
          grad_language_feature_instance_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh,
          grad_scales, grad_rotations, grad_all_map) = _call_native(
-            _C.rasterize_gaussians_backward, native_args, s.debug, "snapshot_bw.dump", "backward")
+            _sunk_backward(ctx.grad_sink), native_args, s.debug, "snapshot_bw.dump", "backward")
+        sunk = set(ctx.grad_sink[0]) if ctx.grad_sink else ()
 
-        def _for(inp, g):
-            # placeholders (empty CPU tensors standing for "absent") never require grad; give autograd None
+        def _for(inp, g, name=None):
+            # placeholders (empty CPU tensors standing for "absent") never require grad; give autograd None.  Gradients the
+            # kernel already wrote into the caller's buffers are not handed to autograd a second time.
+            if name in sunk:
+                return None
             return g if (inp is not None and inp.numel() != 0) else None
 
         return (
-            grad_means3D, grad_means2D, grad_means2D_abs,
-            _for(sh, grad_sh), _for(colors_precomp, grad_colors_precomp),
-            _for(language_feature_precomp, grad_language_feature_precomp) if s.include_feature else None,
-            _for(language_feature_instance_precomp, grad_language_feature_instance_precomp) if s.include_feature else None,
-            grad_opacities, _for(scales, grad_scales), _for(rotations, grad_rotations),
-            _for(cov3Ds_precomp, grad_cov3Ds_precomp), _for(all_maps, grad_all_map) if s.render_geo else None,
-            None,
+            _for(means3D, grad_means3D, "means3D"), grad_means2D, grad_means2D_abs,
+            _for(sh, grad_sh, "sh"), _for(colors_precomp, grad_colors_precomp, "colors"),
+            _for(language_feature_precomp, grad_language_feature_precomp, "language_feature") if s.include_feature else None,
+            _for(language_feature_instance_precomp, grad_language_feature_instance_precomp, "instance_feature")
+            if s.include_feature else None,
+            _for(opacities, grad_opacities, "opacity"), _for(scales, grad_scales, "scales"),
+            _for(rotations, grad_rotations, "rotations"),
+            _for(cov3Ds_precomp, grad_cov3Ds_precomp, "cov3D"),
+            _for(all_maps, grad_all_map, "all_map") if s.render_geo else None,
+            None, None,
         )
+
+
+def _sunk_backward(grad_sink):
+    if not grad_sink:
+        return _C.rasterize_gaussians_backward
+    buffers, accumulate = grad_sink
+
+    def call(*args):
+        return _C.rasterize_gaussians_backward(*args, grad_buffers=buffers, accumulate=accumulate)
+    return call
 
 
 def rasterize_gaussians(means3D, means2D, means2D_abs, sh, colors_precomp, language_feature_precomp,
                         language_feature_instance_precomp, opacities, scales, rotations, cov3Ds_precomp, all_map,
-                        raster_settings):
+                        raster_settings, grad_sink=None):
     return _RasterizeGaussians.apply(means3D, means2D, means2D_abs, sh, colors_precomp, language_feature_precomp,
                                      language_feature_instance_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                                     all_map, raster_settings)
+                                     all_map, raster_settings, grad_sink)
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, *, grad_buffers=None, accumulate=False):
         super().__init__()
         self.raster_settings = raster_settings
+        # multi-view extension: see the module docstring and lsx_b200.ops.rasterize_gaussians_backward
+        self.grad_buffers = grad_buffers
+        self.accumulate = accumulate
 
     def markVisible(self, positions):
         """Boolean mask of the points in front of the near plane (view-space z > 0.2)."""
@@ -146,4 +171,5 @@ class GaussianRasterizer(nn.Module):
         return rasterize_gaussians(
             means3D, means2D, means2D_abs, _absent(shs), _absent(colors_precomp),
             _absent(language_feature_precomp), _absent(language_feature_instance_precomp), opacities,
-            _absent(scales), _absent(rotations), _absent(cov3D_precomp), _absent(all_map), self.raster_settings)
+            _absent(scales), _absent(rotations), _absent(cov3D_precomp), _absent(all_map), self.raster_settings,
+            (self.grad_buffers, bool(self.accumulate)) if self.grad_buffers else None)

@@ -15,7 +15,7 @@ CSRC = os.path.join(ROOT, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "liblsx_b200.so")
 
-SOURCES = ["api.cu", "preprocess.cu", "sort.cu", "binning.cu", "cull.cu", "render_fwd.cu", "render_bwd.cu", "knn.cu", "depth_normal.cu", "image_loss.cu", "arena_adam.cu", "gaussian_head.cu", "densify.cu", "pose.cu", "cls3d.cu", "microbench.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "sort.cu", "binning.cu", "cull.cu", "render_fwd.cu", "render_bwd.cu", "stats.cu", "knn.cu", "depth_normal.cu", "image_loss.cu", "arena_adam.cu", "gaussian_head.cu", "densify.cu", "pose.cu", "cls3d.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wno-attributes",

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("LSX_B200_LIB", os.path.join(_PKG_DIR, "liblsx_b200.so
 
 ALLOC_FN = ctypes.CFUNCTYPE(c_void_p, c_void_p, c_size_t)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_BLEND_CHANNELS = 40
 
 
@@ -121,6 +121,7 @@ EXPORTS = {
                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_gaussian_head_forward": (c_int32, [c_int32] + [c_void_p] * 11),
     "lsx_gaussian_head_backward": (c_int32, [c_int32] + [c_void_p] * 16),
+    "lsx_gaussian_head_backward_acc": (c_int32, [c_int32] + [c_void_p] * 15 + [c_int32, c_void_p]),
     "lsx_densify_stats_update": (c_int32, [c_int32] + [c_void_p] * 9),
     "lsx_densify_workspace_bytes": (c_size_t, [c_int32]),
     "lsx_densify_plan": (c_int32, [POINTER(DensifyPlanArgs), POINTER(DensifyPlanResult)]),
@@ -140,6 +141,7 @@ EXPORTS = {
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
     "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                         c_void_p, c_void_p]),
+    "lsx_render_stats": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lsx_kernel_launch_count": (c_uint64, []),
     "lsx_profile_enable": (None, [c_int32]),
     "lsx_profile_read": (c_int32, [POINTER(c_float), c_int32]),
@@ -147,6 +149,10 @@ EXPORTS = {
     "lsx_last_error": (c_char_p, []),
     "lsx_abi_version": (c_int32, []),
 }
+
+# lsx_backward_args.accumulate_param_grads bits (LSX_ACC_* in the header), by the names ops.py uses for grad_buffers
+ACC_BITS = {"means3D": 0x001, "sh": 0x002, "opacity": 0x004, "scales": 0x008, "rotations": 0x010, "colors": 0x020,
+            "language_feature": 0x040, "instance_feature": 0x080, "all_map": 0x100, "cov3D": 0x200}
 
 _lib = None
 

@@ -240,7 +240,10 @@ def capture(params: GradArena, exp_avg: Optional[GradArena], exp_avg_sq: Optiona
             t = torch.zeros((P, 6 if name == "knn_f" else 0), device=dev)          # knn_f: unused 6-d parameter (:285-287)
         return _REF_SHAPES.get(name, lambda x: x)(t)
 
-    tensors = {n: grp(params, n) for n in _REF_GROUPS}
+    # The reference pickles nn.Parameters and restore() assigns them straight to self._xyz etc. (gaussian_model.py:139-191),
+    # so resumed training only gets gradients if the entries ARE Parameters with the reference's requires_grad flags
+    # (instance_feature starts frozen, gaussian_model.py:301; change_reqiures_grad switches the sets later).
+    tensors = {n: torch.nn.Parameter(grp(params, n), requires_grad=(n != "instance_feature")) for n in _REF_GROUPS}
     # param_groups come from a real torch.optim.Adam over placeholders, so that the dict has exactly the keys this torch
     # version's Adam.load_state_dict expects (the reference builds its optimizer the same way, gaussian_model.py:313-328)
     template = torch.optim.Adam([{"params": [torch.nn.Parameter(torch.empty(0))], "lr": float(lrs.get(n, 0.0)), "name": n}
@@ -251,7 +254,15 @@ def capture(params: GradArena, exp_avg: Optional[GradArena], exp_avg_sq: Optiona
         if exp_avg is not None and w.get(n, 0) > 0:
             state[i] = {"step": torch.tensor(float(step)), "exp_avg": grp(exp_avg, n), "exp_avg_sq": grp(exp_avg_sq, n)}
     opt_dict = {"state": state, "param_groups": groups}
-    cam_dict = cam_optimizer_state if cam_optimizer_state is not None else {"state": {}, "param_groups": []}
+    if cam_optimizer_state is not None:
+        cam_dict = cam_optimizer_state
+    else:
+        # the reference's cam_optimizer has ONE group ("pose", lr = rotation_lr * 0.1, gaussian_model.py:326-330);
+        # load_state_dict rejects a state dict with a different number of groups, so the default is a fresh Adam over P
+        cam_tmpl = torch.optim.Adam([{"params": [torch.nn.Parameter(torch.empty(0))],
+                                      "lr": float(lrs.get("pose", 0.1 * float(lrs.get("rotation", 0.0)))), "name": "pose"}],
+                                    lr=0.0, eps=1e-15)
+        cam_dict = cam_tmpl.state_dict()
     col = lambda t: t.detach().clone().reshape(P, 1)
     head = (active_sh_degree, tensors["xyz"], tensors["knn_f"], tensors["f_dc"], tensors["f_rest"], tensors["scaling"],
             tensors["rotation"], tensors["opacity"])

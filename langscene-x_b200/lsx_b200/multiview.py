@@ -15,8 +15,11 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-# per-Gaussian parameter-gradient groups, in arena order (name, trailing shape as a function of (M, F, Fi))
-PARAM_GROUPS = ("means3D", "sh", "opacity", "scales", "rotations", "language_feature", "instance_feature", "all_map")
+# per-Gaussian parameter-gradient groups, in arena order (name, trailing shape as a function of (M, F, Fi)).
+# `all_map` is NOT a parameter: the render wrapper derives it per view from rotation / scale / position and the camera
+# (field_construction/gaussian_renderer/__init__.py:188-196), so its gradient is consumed by the wrapper's backward on the
+# rank that rendered the view and never crosses ranks (summing it over cameras would be meaningless).
+PARAM_GROUPS = ("means3D", "sh", "opacity", "scales", "rotations", "language_feature", "instance_feature")
 
 
 def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
@@ -28,7 +31,7 @@ def shard_views(n_views: int, world_size: int, rank: int) -> List[int]:
 
 def group_widths(M: int, F: int, Fi: int) -> Dict[str, int]:
     return {"means3D": 3, "sh": 3 * M, "opacity": 1, "scales": 3, "rotations": 4, "language_feature": F,
-            "instance_feature": Fi, "all_map": 5}
+            "instance_feature": Fi}
 
 
 @dataclass
@@ -39,16 +42,26 @@ class GradArena:
     offsets: Dict[str, Tuple[int, int]] = None   # group name -> (first element, element count) inside `flat`
 
     @staticmethod
-    def allocate(P: int, M: int, F: int, Fi: int, device) -> "GradArena":
+    def allocate(P: int, M: int, F: int, Fi: int, device, extra: Dict[str, Tuple[int, ...]] = None) -> "GradArena":
+        """`extra`: further groups that are not per-Gaussian, name -> shape — e.g. {"pose": (n_views, 7)} for the camera-pose
+        gradients of pose optimisation (GaussianModel.P, field_construction/scene/gaussian_model.py:243-262): every rank
+        writes the rows of the views it rendered, the same all-reduce sums them."""
         widths = group_widths(M, F, Fi)
-        offs, total = {}, 0
+        offs, shapes, total = {}, {}, 0
         for name in PARAM_GROUPS:
-            n = P * widths[name]
+            shapes[name] = (P, widths[name])
+        for name, shp in (extra or {}).items():
+            if name in shapes:
+                raise ValueError(f"extra group {name!r} collides with a parameter group")
+            shapes[name] = tuple(int(x) for x in shp)
+        for name, shp in shapes.items():
+            n = 1
+            for x in shp:
+                n *= x
             offs[name] = (total, n)
             total += (n + 63) // 64 * 64  # 256-B aligned groups (float4 stores, NCCL-friendly)
         flat = torch.zeros(max(total, 1), dtype=torch.float32, device=device)
-        views = {name: flat[o:o + n].view(P, widths[name]) if widths[name] else flat[o:o]
-                 for name, (o, n) in offs.items()}
+        views = {name: flat[o:o + n].view(shapes[name]) for name, (o, n) in offs.items()}
         return GradArena(flat, views, offs)
 
     def zero_(self):
@@ -75,6 +88,45 @@ class GradArena:
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
         return None
 
+    def span(self, names: Sequence[str]) -> torch.Tensor:
+        """The contiguous slice of `flat` covering the given groups (they must be adjacent in arena order)."""
+        order = list(self.offsets)
+        idx = sorted(order.index(n) for n in names)
+        if idx != list(range(idx[0], idx[0] + len(idx))):
+            raise ValueError(f"groups {list(names)} are not adjacent in the arena")
+        first = self.offsets[order[idx[0]]][0]
+        last_o, last_n = self.offsets[order[idx[-1]]]
+        end = (last_o + last_n + 63) // 64 * 64 if idx[-1] + 1 < len(order) else self.flat.numel()
+        return self.flat[first:end]
+
+    def all_reduce_spans(self, spans: Sequence[Sequence[str]], group=None) -> "PendingReduce":
+        """Asynchronous all-reduce of the arena in pieces: one collective per span of adjacent groups, issued now in the
+        given order on the process group's communication stream (NCCL: its own stream, which waits for the work already
+        enqueued on the current stream), so that compute enqueued AFTER this call overlaps the transfers.  The caller
+        issues a span as soon as the last kernel that writes it has been enqueued, and calls `.wait()` on the result
+        before the first kernel that reads the reduced values (the optimiser step)."""
+        works = []
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for names in spans:
+                works.append(dist.all_reduce(self.span(names), op=dist.ReduceOp.SUM, group=group, async_op=True))
+        return PendingReduce(works)
+
+
+class PendingReduce:
+    """Handles of collectives in flight; `wait()` makes the CURRENT stream wait for them (no host block with NCCL)."""
+
+    def __init__(self, works=()):
+        self.works = list(works)
+
+    def extend(self, other: "PendingReduce"):
+        self.works.extend(other.works)
+        return self
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+
 
 @dataclass
 class DensifyStats:
@@ -100,16 +152,35 @@ class DensifyStats:
                                        self.max_radii2D)
 
     def all_reduce(self, group=None):
+        """Sum / max over ranks, IN PLACE.  Only ever call this on a per-step DELTA (statistics of the views of one step,
+        started from zero): the persistent statistics are cumulative over a whole densification interval
+        (gaussian_model.py:720-724), so reducing them again every step would count earlier steps world_size times.
+        `multiview_step` does the right thing: delta -> all_reduce -> merge_into(persistent)."""
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
             return
         packed = torch.stack([self.grad_accum, self.grad_accum_abs, self.denom])
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-        self.grad_accum, self.grad_accum_abs, self.denom = packed[0], packed[1], packed[2]
+        self.grad_accum.copy_(packed[0])
+        self.grad_accum_abs.copy_(packed[1])
+        self.denom.copy_(packed[2])
         dist.all_reduce(self.max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+    def zero_(self):
+        for t in (self.grad_accum, self.grad_accum_abs, self.denom, self.max_radii2D):
+            t.zero_()
+        return self
+
+    def merge_into(self, total: "DensifyStats"):
+        """Fold this (all-reduced) per-step delta into the persistent statistics: sums add, radii take the maximum."""
+        total.grad_accum += self.grad_accum
+        total.grad_accum_abs += self.grad_accum_abs
+        total.denom += self.denom
+        torch.maximum(total.max_radii2D, self.max_radii2D, out=total.max_radii2D)
+        return total
 
 
 BWD_TO_GROUP = {"means3D": "means3D", "sh": "sh", "opacity": "opacity", "scales": "scales", "rotations": "rotations",
-                "language_feature": "language_feature", "instance_feature": "instance_feature", "all_map": "all_map"}
+                "language_feature": "language_feature", "instance_feature": "instance_feature"}
 
 
 def accumulate_views(render_view, view_ids: Sequence[int], arena: GradArena, stats: DensifyStats = None
@@ -128,13 +199,22 @@ def accumulate_views(render_view, view_ids: Sequence[int], arena: GradArena, sta
     return arena, n
 
 
-def multiview_step(render_view, n_views: int, arena: GradArena, stats: DensifyStats = None, group=None):
-    """One optimisation step's gradient: local views -> arena -> one all-reduce.  Returns #local views."""
+def multiview_step(render_view, n_views: int, arena: GradArena, stats: DensifyStats = None, group=None,
+                   _delta: DensifyStats = None):
+    """One optimisation step's gradient: local views -> arena -> one all-reduce.  Returns #local views.
+
+    `stats` are the PERSISTENT densification statistics (cumulative over the steps of a densification interval): the
+    step's views go into a zeroed per-step delta, the delta is all-reduced, and only then folded into `stats` — so after
+    every step each rank holds exactly what single-process accumulation over all views of all steps so far would hold."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     arena.zero_()
-    _, n_local = accumulate_views(render_view, shard_views(n_views, world, rank), arena, stats)
+    delta = None
+    if stats is not None:
+        delta = _delta.zero_() if _delta is not None else DensifyStats.allocate(stats.denom.numel(), stats.denom.device)
+    _, n_local = accumulate_views(render_view, shard_views(n_views, world, rank), arena, delta)
     arena.all_reduce(group)
     if stats is not None:
-        stats.all_reduce(group)
+        delta.all_reduce(group)
+        delta.merge_into(stats)
     return n_local

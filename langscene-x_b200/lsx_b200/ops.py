@@ -46,20 +46,40 @@ class _ScratchAlloc:
     released by reference counting when the caller drops it."""
 
     def __init__(self, device):
-        holder = []
+        holder, failure = [], []
 
         def _cb(_user, nbytes):
-            t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            # ctypes swallows exceptions raised inside a callback (the C side would just see NULL): keep the exception —
+            # typically torch.cuda.OutOfMemoryError, which training loops catch to empty the cache and retry — and let
+            # `reraise()` surface it with its type once the library has returned its "allocation failed" status.
+            try:
+                t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            except Exception as e:  # noqa: BLE001
+                failure[:] = [e]
+                return 0
             holder[:] = [t]
             return t.data_ptr()
 
         self._holder = holder
+        self._failure = failure
         self._device = device
         self.fn = _lib.ALLOC_FN(_cb)
 
     @property
     def tensor(self):
         return self._holder[0] if self._holder else torch.empty(0, dtype=torch.uint8, device=self._device)
+
+    def reraise(self):
+        if self._failure:
+            raise self._failure[0]
+
+
+def _check(status, what, *allocs):
+    """status -> exception; an allocation failure inside a scratch callback is re-raised with its original type."""
+    if status != 0:
+        for a in allocs:
+            a.reraise()
+    _lib.check(status, what)
 
 
 def _stream_handle(device):
@@ -140,7 +160,7 @@ def rasterize_gaussians(
         a.geom_alloc, a.binning_alloc, a.image_alloc = geom.fn, binning.fn, image.fn
         a.stream = _stream_handle(device)
         rendered = ctypes.c_int32(0)
-        _lib.check(lib.lsx_rasterize_forward(ctypes.byref(a), ctypes.byref(rendered)), "rasterize_gaussians")
+        _check(lib.lsx_rasterize_forward(ctypes.byref(a), ctypes.byref(rendered)), "rasterize_gaussians", geom, binning, image)
 
     return (int(rendered.value), out_color, out_lang, out_inst, radii, out_observe, out_all_map, out_plane_depth,
             geom.tensor, binning.tensor, image.tensor)
@@ -171,7 +191,8 @@ def rasterize_gaussians_backward(
     multi-view optimisation: `grad_buffers` maps any of {"means3D", "sh", "opacity", "scales", "rotations", "colors",
     "language_feature", "instance_feature", "all_map", "cov3D"} to a caller-owned contiguous fp32 tensor (e.g. a view
     into lsx_b200.multiview.GradArena) that receives that gradient instead of a fresh tensor; with `accumulate=True`
-    the parameter gradients are ADDED to those buffers (the kernel does the read-modify-write, no extra pass)."""
+    the gradients of exactly those groups are ADDED to the buffers (the kernel does the read-modify-write, no extra pass);
+    all other outputs are fresh tensors holding this view's gradient."""
     lib = _lib.load()
     if not means3D.is_cuda:
         raise RuntimeError("means3D must be a CUDA tensor (this operator has no CPU path)")
@@ -229,14 +250,12 @@ def rasterize_gaussians_backward(
             (g_means3D, g_sh, g_opacity, g_scales, g_rot, g_colors, g_lang, g_inst, g_all_map, g_cov3D) = (
                 own[k] for k in ("means3D", "sh", "opacity", "scales", "rotations", "colors", "language_feature",
                                  "instance_feature", "all_map", "cov3D"))
+        acc_mask = 0
         if accumulate:
             if not grad_buffers:
                 raise RuntimeError("accumulate=True needs caller-owned grad_buffers to accumulate into")
-            for name, t in (("means3D", g_means3D), ("sh", g_sh), ("opacity", g_opacity), ("scales", g_scales),
-                            ("rotations", g_rot), ("colors", g_colors), ("language_feature", g_lang),
-                            ("instance_feature", g_inst), ("all_map", g_all_map), ("cov3D", g_cov3D)):
-                if name not in grad_buffers:
-                    t.zero_()  # library-owned outputs start from zero so that "+=" equals "="
+            for name in grad_buffers:       # only the caller's buffers are added to; library-owned outputs are overwritten
+                acc_mask |= _lib.ACC_BITS[name]
 
         if P != 0:
             a = _lib.BackwardArgs()
@@ -261,7 +280,7 @@ def rasterize_gaussians_backward(
             a.dL_dsh = g_sh.data_ptr() if M > 0 else None
             a.dL_dscales, a.dL_drotations, a.dL_dall_map = g_scales.data_ptr(), g_rot.data_ptr(), g_all_map.data_ptr()
             a.stream = _stream_handle(device)
-            a.accumulate_param_grads = int(bool(accumulate))
+            a.accumulate_param_grads = acc_mask
             _lib.check(lib.lsx_rasterize_backward(ctypes.byref(a)), "rasterize_gaussians_backward")
 
     return (g_means2D, g_means2D_abs, g_colors, g_lang, g_inst, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot,
@@ -296,8 +315,24 @@ def distCUDA2(points):
         means = torch.empty((P,), dtype=_FLOAT, device=device)
         if P != 0:
             scratch = _ScratchAlloc(device)
-            _lib.check(lib.lsx_knn_mean_dist2(P, points.data_ptr(), means.data_ptr(), scratch.fn, None,
-                                              _stream_handle(device)), "distCUDA2")
+            _check(lib.lsx_knn_mean_dist2(P, points.data_ptr(), means.data_ptr(), scratch.fn, None,
+                                          _stream_handle(device)), "distCUDA2", scratch)
             # `scratch.tensor` may be released now: the caching allocator keeps the block alive for work
             # already enqueued on this stream.
     return means
+
+
+def render_stats(num_rendered, geomBuffer, binningBuffer, imageBuffer, P, image_height, image_width, n_blend_channels):
+    """Workload counters of the view a forward call just rendered, counted on the device (one 64-byte read back):
+    dict(S=(pixel, entry) tests per pass of the reference's render loops = sum of n_contrib, B=(pixel, entry) blends,
+    V=(8x4 block, entry) visits of this library's backward, Vb=visits in which some pixel blends, L=total length of the
+    per-block compacted lists, R=num_rendered).  SURVEY.md 8d: S, B and R accompany every reported number."""
+    lib = _lib.load()
+    device = geomBuffer.device
+    with torch.cuda.device(device):
+        out = torch.empty(8, dtype=torch.int64, device=device)
+        _lib.check(lib.lsx_render_stats(int(P), int(image_width), int(image_height), int(num_rendered), int(n_blend_channels),
+                                        _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), out.data_ptr(),
+                                        _stream_handle(device)), "render_stats")
+        v = out.cpu().tolist()
+    return {"S": v[0], "B": v[1], "V": v[2], "Vb": v[3], "L": v[4], "R": int(num_rendered)}

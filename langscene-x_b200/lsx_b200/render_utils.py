@@ -135,6 +135,7 @@ class _PoseTransform(torch.autograd.Function):
         P = int(xyz.shape[0])
         if pose.numel() != 7 or xyz.shape != (P, 3) or (rotation_raw is not None and rotation_raw.shape != (P, 4)):
             raise RuntimeError("expected pose (7,) = [quaternion | translation], xyz (P,3), rotation (P,4)")
+        ctx.pose_shape = pose.shape          # a caller may pass a (1, 7) row slice such as P[idx:idx + 1]
         pose, xyz = pose.reshape(7).contiguous(), xyz.contiguous()
         rot = None if rotation_raw is None else rotation_raw.contiguous()
         dev = xyz.device
@@ -145,7 +146,6 @@ class _PoseTransform(torch.autograd.Function):
                                                               out_xyz.data_ptr(), None if rot is None else out_rot.data_ptr(),
                                                               _stream(dev)), "pose_transform")
         ctx.save_for_backward(pose, xyz, rot if rot is not None else torch.empty(0, device=dev))
-        ctx.pose_shape = pose.shape
         if rot is None:
             return out_xyz, torch.empty(0, device=dev)
         return out_xyz, out_rot
@@ -167,7 +167,7 @@ class _PoseTransform(torch.autograd.Function):
             _lib.check(lib.lsx_pose_transform_backward(P, pose.data_ptr(), xyz.data_ptr(), dp(rot) if has_rot else None, dp(g_xyz),
                                                        dp(g_rot), d_xyz.data_ptr(), dp(d_rot), d_pose.data_ptr(),
                                                        partials.data_ptr(), _stream(dev)), "pose_transform backward")
-        return d_pose, d_xyz, d_rot
+        return d_pose.view(ctx.pose_shape), d_xyz, d_rot
 
 
 def pose_transform(camera_pose, xyz, rotation_raw=None):

@@ -76,6 +76,38 @@ def test_restore_reads_reference_checkpoint_and_capture_mirrors_it():
     torch.optim.Adam([torch.nn.Parameter(t.clone()) for t in (mine[1], mine[2])], lr=0.0)  # tensors are usable as parameters
 
 
+def test_capture_round_trips_through_the_reference_restore_sequence():
+    """the tuple must survive GaussianModel.restore(mode='train') (gaussian_model.py:139-191): the entries are
+    assigned to self._xyz etc. AS THEY ARE (so they must be Parameters that require grad), then training_setup builds a
+    9-group Adam and a 1-group camera Adam and both load_state_dict calls must accept the captured dicts."""
+    from lsx_b200.io_formats import capture, restore
+    ref_tuple, _ = torch.load(os.path.join(GOLD_DIR, "checkpoint_ref.pth"), weights_only=False)
+    st = restore(ref_tuple, "cpu")
+    for cam_state in (st["cam_optimizer_state"], None):                       # the reference's dict, and our default
+        tup = capture(st["params"], st["exp_avg"], st["exp_avg_sq"], st["stats"], st["active_sh_degree"], st["step"], st["lrs"],
+                      st["spatial_lr_scale"], st["poses"], cam_state, include_feature=True)
+        (_deg, xyz, knn_f, f_dc, f_rest, scaling, rotation, opacity, lang, inst, _mr, _mw, _a, _aa, _d, _da, opt_dict, cam_dict,
+         _sls, P) = tup
+        named = [("xyz", xyz), ("knn_f", knn_f), ("f_dc", f_dc), ("f_rest", f_rest), ("opacity", opacity), ("scaling", scaling),
+                 ("rotation", rotation), ("language_feature", lang), ("instance_feature", inst)]
+        for n, t in named:                                                    # restore(): self._xyz = <tuple entry>
+            assert isinstance(t, torch.nn.Parameter), n
+            assert t.requires_grad == (n != "instance_feature"), n
+        optimizer = torch.optim.Adam([{"params": [t], "lr": 1e-3, "name": n} for n, t in named], lr=0.0, eps=1e-15)
+        poses = P.detach().clone().requires_grad_(True)
+        cam_optimizer = torch.optim.Adam([{"params": [poses], "lr": 1e-4, "name": "pose"}], lr=0.0, eps=1e-15)
+        optimizer.load_state_dict(opt_dict)                                   # training_setup + load_state_dict (:186-191)
+        cam_optimizer.load_state_dict(cam_dict)
+        before = xyz.detach().clone()
+        loss = sum((t ** 2).sum() for n, t in named if t.requires_grad and t.numel()) + (poses ** 2).sum()
+        loss.backward()
+        assert xyz.grad is not None and inst.grad is None
+        optimizer.step()
+        cam_optimizer.step()
+        assert not torch.equal(xyz.detach(), before)                          # resumed training really trains
+        assert float(optimizer.state[xyz]["step"]) == st["step"] + 1          # moments were picked up, not re-created
+
+
 def test_ply_header_and_reader_known_answer(tmp_path):
     """Byte-level KAT of the layout plyfile produces for an all-'f4' vertex element (restated: plyfile is absent)."""
     from lsx_b200.io_formats import ply_attributes, ply_header, read_ply_vertices

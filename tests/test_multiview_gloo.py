@@ -25,11 +25,45 @@ def fake_view(v):
     return fwd, bwd
 
 
+STEPS = 3
+
+
+def fake_view_of_step(step):
+    return lambda v: fake_view(1000 * step + v)
+
+
 def single_process_reference():
     arena, stats = GradArena.allocate(P, M, F, FI, "cpu"), DensifyStats.allocate(P, "cpu")
     n = multiview_step(fake_view, V, arena, stats)
     assert n == V
     return arena, stats
+
+
+def single_process_steps():
+    """Persistent statistics after STEPS steps of V views each, accumulated by one process (the reference's semantics)."""
+    arena, stats = GradArena.allocate(P, M, F, FI, "cpu"), DensifyStats.allocate(P, "cpu")
+    for s in range(STEPS):
+        multiview_step(fake_view_of_step(s), V, arena, stats)
+    return arena, stats
+
+
+def _worker_steps(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    arena, stats = GradArena.allocate(P, M, F, FI, "cpu", extra={"pose": (V, 7)}), DensifyStats.allocate(P, "cpu")
+    for s in range(STEPS):
+        multiview_step(fake_view_of_step(s), V, arena, stats)
+    # piecewise asynchronous reduction of the same arena must give what the single collective gives
+    a2 = GradArena.allocate(P, M, F, FI, "cpu", extra={"pose": (V, 7)})
+    a2.flat.copy_(torch.arange(a2.flat.numel(), dtype=torch.float32) * (rank + 1))
+    pend = a2.all_reduce_spans([["sh"], ["means3D"], ["opacity", "scales", "rotations"],
+                                ["language_feature", "instance_feature", "pose"]])
+    pend.wait()
+    expect = torch.arange(a2.flat.numel(), dtype=torch.float32) * sum(r + 1 for r in range(world))
+    torch.save((rank, arena.flat.clone(), stats.grad_accum.clone(), stats.grad_accum_abs.clone(), stats.denom.clone(),
+                stats.max_radii2D.clone(), bool(torch.equal(a2.flat, expect))), os.path.join(q, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def _worker(rank, world, port, q):
@@ -82,3 +116,43 @@ def test_two_rank_allreduce_equals_single_process_accumulation():
         assert torch.allclose(gaa, ref_stats.grad_accum_abs, rtol=1e-6, atol=1e-6)
         assert torch.equal(den, ref_stats.denom) and torch.equal(mr, ref_stats.max_radii2D)
     assert torch.equal(results[0][2], results[1][2])          # bitwise identical across ranks
+
+
+def test_statistics_stay_cumulative_over_steps():
+    """the persistent statistics are cumulative; only the per-step delta may be all-reduced.  Three steps on two
+    ranks must equal three steps of single-process accumulation (they grew by world_size per step before the fix)."""
+    _, ref_stats = single_process_steps()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    import tempfile
+    ctx = mp.get_context("spawn")
+    with tempfile.TemporaryDirectory() as q:
+        procs = [ctx.Process(target=_worker_steps, args=(r, 2, port, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=180)
+            assert p.exitcode == 0
+        results = [torch.load(os.path.join(q, f"rank{r}.pt")) for r in range(2)]
+    for _, _, ga, gaa, den, mr, spans_ok in results:
+        assert torch.allclose(ga, ref_stats.grad_accum, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(gaa, ref_stats.grad_accum_abs, rtol=1e-5, atol=1e-6)
+        assert torch.equal(den, ref_stats.denom) and torch.equal(mr, ref_stats.max_radii2D)
+        assert spans_ok
+
+
+def test_arena_spans_and_extra_groups():
+    a = GradArena.allocate(P, M, F, FI, "cpu", extra={"pose": (V, 7)})
+    assert a.views["pose"].shape == (V, 7) and "all_map" not in a.views
+    whole = a.span(list(a.offsets))
+    assert whole.data_ptr() == a.flat.data_ptr() and whole.numel() == a.flat.numel()
+    pieces = [a.span([n]) for n in a.offsets]
+    assert sum(p.numel() for p in pieces) == a.flat.numel()            # the spans tile the arena, padding included
+    for x, y in zip(pieces[:-1], pieces[1:]):
+        assert x.data_ptr() + 4 * x.numel() == y.data_ptr()
+    try:
+        a.span(["means3D", "opacity"])
+        raise AssertionError("non-adjacent groups must be rejected")
+    except ValueError:
+        pass
