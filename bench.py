@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench.py — fwd+bwd throughput of the rasterizer hot path on BASELINE.json's headline configuration.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference|reference-cpu] [--config C3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl new|reference|reference-cpu] [--config C3|C4-loop|C5-stress]
+
+(--config C4-loop / C5-stress: BASELINE configs 4 and 5 — the whole optimisation iteration, sharded; see bench_loop.py.)
 
 A "step" is one optimisation step's gradient on every GPU: forward + backward of `--views-per-gpu` (default 8)
 1920x1080 views of the 1M-Gaussian synthetic scene (16-d language feature + instance feature +
@@ -35,11 +37,25 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 METRIC = "fwd+bwd MPix/s (1M Gaussians, 1920x1080, 16-d language feature + normal + depth)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-# (profiles/r5m_ncu_render_kernels.md: the render kernels as shipped at the end of round 1)
-NCU_TRAFFIC = {"render_bwd": 651566080, "render_fwd": 448174848}
-# smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture: what actually bounds these kernels
-NCU_ISSUE_BUSY_PCT = {"render_bwd": 74.7, "render_fwd": 86.8}
+
+
+def ncu_record():
+    """dram bytes / issue-slot utilisation of the render kernels from the committed `ncu --set full` capture, stamped with
+    the sha1 of the kernel sources they were captured from (profiles/ncu_render_kernels.json, written by
+    tools/ncu_summary.py).  A capture of OTHER sources is reported as stale: traffic = null, never a stale number."""
+    import hashlib
+    path = os.path.join(REPO, "profiles", "ncu_render_kernels.json")
+    if not os.path.exists(path):
+        return None, "no committed capture (profiles/ncu_render_kernels.json)"
+    with open(path) as f:
+        rec = json.load(f)
+    h = hashlib.sha1()
+    for name in ("render_fwd.cu", "render_bwd.cu", "tile_stage.cuh"):
+        with open(os.path.join(REPO, "langscene-x_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    if rec.get("sources_sha1") != h.hexdigest():
+        return None, f"stale: captured from sources {str(rec.get('sources_sha1'))[:12]}, tree has {h.hexdigest()[:12]}"
+    return rec, "profiles/" + rec.get("capture", "ncu_render_kernels.json")
 
 
 def load_peaks():
@@ -284,8 +300,9 @@ def e2e_stepper(mod, views, grads, arena, world):
 
 
 def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
-    """Same, through the public nn.Module + autograd (the call a LangScene-X user makes); autograd accumulates the
-    views' gradients in the parameters' .grad, which are then packed into the arena for the all-reduce."""
+    """Same, through the public nn.Module + autograd (the call a LangScene-X user makes).  The rasterizer's inputs are the
+    leaves here, so the module's multi-view extension hands the arena to the backward kernel: every view's parameter
+    gradients are written / added in place (no .grad tensors, no zero + add passes), then one all-reduce."""
     from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     feeder = HostFeeder(views, grads)
     leaf = lambda t: t.detach().clone().requires_grad_(True)
@@ -296,9 +313,10 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
     m2 = torch.zeros_like(scene.means3D, requires_grad=True)
     m2a = torch.zeros_like(scene.means3D, requires_grad=True)
     c0 = views[0]["cam"]
+    sink = arena.grad_buffers()
 
     def step():
-        for p in list(params.values()) + ams + [m2, m2a]:
+        for p in ams + [m2, m2a]:
             p.grad = None
         acc = None
         feeder.fetch(0)
@@ -308,10 +326,10 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
             d_cam, d_gcol = feeder.get(i)
             s = GaussianRasterizationSettings(c0.H, c0.W, c0.tanfovx, c0.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
                                               d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
-            out = GaussianRasterizer(s)(means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"],
-                                        shs=params["shs"], language_feature_precomp=params["lang"],
-                                        language_feature_instance_precomp=params["inst"], scales=params["scales"],
-                                        rotations=params["rots"], all_map=am)
+            out = GaussianRasterizer(s, grad_buffers=sink, accumulate=i > 0)(
+                means3D=params["means3D"], means2D=m2, means2D_abs=m2a, opacities=params["opac"], shs=params["shs"],
+                language_feature_precomp=params["lang"], language_feature_instance_precomp=params["inst"],
+                scales=params["scales"], rotations=params["rots"], all_map=am)
             color, lf, li, _, _, amap, depth = out
             torch.autograd.backward([color, lf, li, amap, depth],
                                     [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
@@ -319,12 +337,8 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
             feeder.release(i)
             acc = color.sum() if acc is None else acc + color.sum()
         if world > 1:
-            arena.zero_()
-            arena.accumulate({"means3D": params["means3D"].grad, "sh": params["shs"].grad, "opacity": params["opac"].grad,
-                              "scales": params["scales"].grad, "rotations": params["rots"].grad,
-                              "language_feature": params["lang"].grad, "instance_feature": params["inst"].grad})
             arena.all_reduce()
-        return torch.stack([acc, params["means3D"].grad.sum()]).to("cpu")
+        return torch.stack([acc, arena.views["means3D"].sum()]).to("cpu")
     return step, feeder.h2d_bytes, 8
 
 
@@ -371,12 +385,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="new", choices=["new", "reference", "reference-cpu"])
-    ap.add_argument("--config", default="C3")
-    ap.add_argument("--views-per-gpu", type=int, default=8,
-                    help="views rendered by every GPU per step (8 x 8 GPUs = the 64-view batch of BASELINE config 5)")
+    ap.add_argument("--config", default="C3", help="C1..C5 (rasterizer fwd+bwd; C3 = headline) | C4-loop | C5-stress (bench_loop.py)")
+    ap.add_argument("--views-per-gpu", type=int, default=None,
+                    help="views rendered by every GPU per step (default 8: 8 x 8 GPUs = the 64-view batch of BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="loop configs: one blocking all-reduce instead of per-group async ones")
+    ap.add_argument("--no-parity", action="store_true", help="loop configs, N > 1: skip the untimed all-reduce parity check")
+    ap.add_argument("--knn", action="store_true", help="loop configs: also time distCUDA2 over the scene's points")
     args = ap.parse_args()
-    V = max(1, args.views_per_gpu)
+    args.views_per_gpu_set = args.views_per_gpu is not None
+    V = max(1, args.views_per_gpu if args.views_per_gpu_set else 8)
     # Untimed warm-up: at least 3 steps and at least 16 single-view passes, so that torch's caching allocator has
     # created every segment it needs (cudaMalloc costs 5-40 ms) before the timed region starts.
     warmup = max(args.warmup, 3, -(-16 // V))
@@ -407,9 +425,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
+    if args.config in ("C4-loop", "C5-stress"):
+        import bench_loop
+        bench_loop.run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     import harness as hz
-    from lsx_b200 import _lib, ops
-    from lsx_b200.multiview import GradArena
+    from lsx_b200.multiview import GradArena     # pure torch; the reference arm never loads liblsx_b200.so
+    new = args.impl == "new"
+    if new:
+        from lsx_b200 import _lib, ops
 
     hbm_peak, peak_src, peaks_json = load_peaks()
     c, scene, grads, bg, views = build_views(args.config, device, rank, world, V)
@@ -417,7 +444,7 @@ def main():
     M, Fi = 16, 3
     Ct = 3 + F + Fi + 5
 
-    if args.impl == "reference":
+    if not new:
         mod = hz.ref_rast_for(F)
         if mod is None:
             if rank == 0:
@@ -428,17 +455,17 @@ def main():
     arena = GradArena.allocate(P, M, F, Fi, device)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # runs through both timed regions
-    # ---- per-view statistics (untimed) ------------------------------------------------------------------
+    # ---- per-view statistics (untimed): R, P_vis, and S / B / visits counted on the device ------------------
     stats_views = []
     for i, vw in enumerate(views):
         fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*vw["fargs"])))
         torch.cuda.synchronize()
         st = {"yaw": round(vw["yaw"], 3), "R": int(fwd["num_rendered"]), "P_vis": int((fwd["radii"] > 0).sum())}
-        if i == 0:
-            if args.impl == "new":
-                nbuf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, st["R"], W, H, Ct)
-            else:
-                nbuf = hz.parse_ref_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, st["R"], W, H)
+        if new:
+            rs = ops.render_stats(fwd["num_rendered"], fwd["geom"], fwd["binning"], fwd["img"], P, H, W, Ct)
+            st.update({k: rs[k] for k in ("S", "B", "V", "Vb", "L")})
+        elif i == 0:
+            nbuf = hz.parse_ref_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, st["R"], W, H)
             st["S"] = int(nbuf["n_contrib"].long().sum())
             del nbuf
         stats_views.append(st)
@@ -447,16 +474,16 @@ def main():
 
     # ---- device-resident timing ----------------------------------------------------------------------
     step = batch_stepper(mod, views, grads, arena, world)
-    launches0 = _lib.kernel_launch_count()
+    launches0 = _lib.kernel_launch_count() if new else 0
     step_detail = {}
     ms_total = time_loop(step, args.steps, warmup, world, step_detail)
-    launches = (_lib.kernel_launch_count() - launches0) if args.impl == "new" else 0
+    launches = (_lib.kernel_launch_count() - launches0) if new else 0
     ms_step = ms_total / args.steps
     mpix = world * V * W * H / (ms_step * 1e-3) / 1e6
 
     # ---- per-stage device times (separate short run so the event hooks do not touch the headline number) ----
     stages = {}
-    if args.impl == "new":
+    if new:
         _lib.profile_enable(True)
         for _ in range(2):
             step()
@@ -465,7 +492,7 @@ def main():
         _lib.profile_enable(False)
 
     # ---- end-to-end through the public API with host buffers ---------------------------------------------------
-    if args.impl == "new":
+    if new:
         estep, h2d, d2h = module_e2e_stepper(scene, views, grads, bg, F, arena, world)
     else:
         estep, h2d, d2h = e2e_stepper(mod, views, grads, arena, world)
@@ -473,8 +500,11 @@ def main():
     clocks = sampler.stop() if sampler else None
     e2e = {"value": world * V * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
            "ms_per_iter": ms_e2e / V, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if args.impl == "new"
-                  else "reference _C.rasterize_gaussians/_backward (pybind)"}
+           "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if new
+                  else "reference _C.rasterize_gaussians/_backward (pybind)",
+           "d2h_note": "training-shaped step: the rendered images are consumed on the device (upstream gradients come from the "
+                       "host instead of a loss), so only two scalars — a checksum of the images and of the position gradients — "
+                       "leave the GPU each step"}
 
     if rank != 0:
         if world > 1:
@@ -499,44 +529,59 @@ def main():
                    "l2": "per-view working set (~1.6 GB of inputs, records, lists, images, gradients) exceeds the 126 MB L2; no flush needed",
                    "upstream_grads": "fixed N(0,1)/(W*H) tensors, no loss inside the timed region"},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "stats": {"P_vis": P_vis, "R": R, "S": S, "Ct": Ct, "per_view": stats_views},
+        "stats": {"P_vis": P_vis, "R": R, "S": S, "B": stats_views[0].get("B"), "Ct": Ct, "per_view": stats_views,
+                  "what": "S = (pixel, entry) tests per render pass of the reference's loops = sum of n_contrib; B = (pixel, entry) "
+                          "blends; V = (8x4 block, entry) visits of this library's backward; Vb = visits in which a pixel blends; "
+                          "L = total length of the per-block lists; counted on the device by lsx_render_stats"},
         "stages_ms": stages,
     }
-    # roofline of the dominant kernel (live stage times, per launch = per view; view 0's sizes)
+    # roofline of the dominant kernel (live stage times, per launch = per view; means over this rank's views)
     if stages:
         dom = max(("render_fwd", "render_bwd"), key=lambda k: stages.get(k, 0.0))
-        Rm = sum(st["R"] for st in stats_views) / len(stats_views)
-        Pm = sum(st["P_vis"] for st in stats_views) / len(stats_views)
-        rec = Rm * (28 + 4 * Ct)
-        kbytes = rec + W * H * 4 * (Ct + 1 + 2) if dom == "render_fwd" else rec + W * H * 4 * ((Ct + 1) + 5 + 2) + Pm * 4 * (Ct + 8)
-        ach = kbytes / (stages[dom] * 1e-3) / 1e9
-        out["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                           "frac": ach / hbm_peak, "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
-                           "launch_ms": stages[dom], "issue_slots_busy_pct_ncu": NCU_ISSUE_BUSY_PCT,
-                           "note": "the render kernels are FP32 instruction-issue bound, not HBM bound (DESIGN.md 3, profiles/): "
-                                   "algorithmic bytes per launch = R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd), "
-                                   "means over this rank's views; `traffic` = dram bytes of one ncu --set full capture of view 0"}
-        it_bytes = fwd_b + bwd_b
-        out["roofline_iteration"] = {"bound": "hbm", "algorithmic_bytes": it_bytes,
-                                     "achieved": it_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": it_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak}
+        mean = lambda k: sum(st[k] for st in stats_views) / len(stats_views)
+        Rm, Pm, Sm, Bm = mean("R"), mean("P_vis"), mean("S"), mean("B")
+        peaks = {}
         try:
             import ctypes
             scratch = torch.empty(64 << 20, dtype=torch.uint8, device=device)
-            res = {}
             for kind, name in ((0, "fp32_ffma_tflops"), (1, "mufu_ex2_gops"), (2, "red_add_f32_gops")):
                 val = ctypes.c_double(0)
                 _lib.check(_lib.load().lsx_microbench(kind, scratch.data_ptr(), scratch.numel(), ctypes.byref(val),
                                                       torch.cuda.current_stream().cuda_stream), "microbench")
-                res[name] = val.value
-            out["peaks"] = res
-            # flops model of SURVEY.md 8d with B unknown: lower bound from the per-test work only
-            out["fp32"] = {"tests_S": S, "flops_lower_bound": 14 * S + 16 * S,
-                           "achieved_tflops_lower_bound": (30 * S) / ((stages["render_fwd"] + stages["render_bwd"]) * 1e-3) / 1e12,
-                           "peak_tflops": res["fp32_ffma_tflops"]}
-        except Exception as e:  # microbench is informative only
-            out["peaks"] = {"error": str(e)[:200]}
-    if args.impl == "new" and world == 1:
+                peaks[name] = val.value
+            del scratch
+        except Exception as e:  # noqa: BLE001
+            peaks = {"error": str(e)[:200]}
+        out["peaks"] = peaks
+        fp32_peak = peaks.get("fp32_ffma_tflops") or 2 * 128 * 148 * 1.965e-3
+        fp32_src = ("measured live: lsx_microbench FFMA (MEASURED_PEAKS.json has no fp32 figure)" if "fp32_ffma_tflops" in peaks
+                    else "theoretical 2 x 128 x 148 SMs x 1.965 GHz")
+        # SURVEY.md 8d flop model: per (pixel, entry) test + per blend
+        flops = {"render_fwd": 14 * Sm + (3 + 2 * Ct) * Bm, "render_bwd": 16 * Sm + (52 + 8 * Ct) * Bm}
+        ncu, ncu_src = ncu_record()
+        for name in ("render_fwd", "render_bwd"):
+            if name not in stages:
+                continue
+            tf = flops[name] / (stages[name] * 1e-3) / 1e12
+            obj = {"kernel": name + "_kernel", "bound": "fp32", "achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                   "frac": tf / fp32_peak, "traffic": (ncu or {}).get(name, {}).get("dram_bytes"),
+                   "issue_slots_pct": (ncu or {}).get(name, {}).get("issue_active_pct"), "ncu_capture": ncu_src,
+                   "peak_source": fp32_src, "launch_ms": stages[name], "flops_per_launch": flops[name],
+                   "flop_model": ("14*S + (3 + 2*Ct)*B" if name == "render_fwd" else "16*S + (52 + 8*Ct)*B") +
+                                 f" (SURVEY.md 8d) with S={Sm:.0f}, B={Bm:.0f}, Ct={Ct}: means over this rank's views"}
+            out["roofline" if name == dom else "roofline_" + name] = obj
+        rec = Rm * (28 + 4 * Ct)
+        kbytes = rec + W * H * 4 * (Ct + 1 + 2) if dom == "render_fwd" else rec + W * H * 4 * ((Ct + 1) + 5 + 2) + Pm * 4 * (Ct + 8)
+        ach = kbytes / (stages[dom] * 1e-3) / 1e9
+        out["roofline_hbm"] = {"kernel": dom + "_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": ach / hbm_peak, "peak_source": peak_src, "algorithmic_bytes": kbytes,
+                               "note": "the same kernel against the HBM roof: R*(28+4*Ct) + pixel planes (+ P_vis*(Ct+8)*4 for bwd); "
+                                       "it is FP32-issue bound (DESIGN.md 3), this view only shows how far from the memory roof it is"}
+        it_bytes = fwd_b + bwd_b
+        out["roofline_iteration"] = {"bound": "hbm", "algorithmic_bytes": it_bytes,
+                                     "achieved": it_bytes / (ms_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": it_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak}
+    if new and world == 1:
         ref = hz.ref_rast_for(F)
         if ref is not None:
             rstep = batch_stepper(ref, views, grads, arena, 1)

@@ -116,7 +116,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _for(language_feature_precomp, grad_language_feature_precomp, "language_feature") if s.include_feature else None,
             _for(language_feature_instance_precomp, grad_language_feature_instance_precomp, "instance_feature")
             if s.include_feature else None,
-            _for(opacities, grad_opacities, "opacity"), _for(scales, grad_scales, "scales"),
+            _for(means3D, grad_opacities, "opacity"), _for(scales, grad_scales, "scales"),   # opacities: always present
             _for(rotations, grad_rotations, "rotations"),
             _for(cov3Ds_precomp, grad_cov3Ds_precomp, "cov3D"),
             _for(all_maps, grad_all_map, "all_map") if s.render_geo else None,

@@ -1,0 +1,206 @@
+"""GPU tier: the view-sharded optimisation step (lsx_b200.field_loop.FieldLoop) — its hand-chained backward, which writes
+every parameter gradient straight into the flat arena, against the SAME operators composed through torch autograd; the
+device-side workload counters (lsx_render_stats) against a brute-force count; the nn.Module's gradient sink; mark_visible
+against the reference's own export."""
+import pytest
+import torch
+
+import harness as hz
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _mixed(a, b):
+    a, b = a.double(), b.double()
+    rms = float(b.pow(2).mean().sqrt())
+    return float(((a - b).abs() / (b.abs() + rms + 1e-30)).max())
+
+
+def _case(P=20_000, W=208, H=144, F=3, n_views=3):
+    import bench_loop as bl
+    from lsx_b200.synthetic import make_scene
+    scene = make_scene(P, W, H, F=F, seed=5).to(DEV)
+    raw = bl.make_raw(scene)
+    views = [bl.make_view(v, n_views, W, H, F, DEV) for v in range(n_views)]
+    poses = bl.make_poses(n_views, DEV)
+    return raw, views, poses
+
+
+def _autograd_gradient(raw, views, poses, cfg, sample_idx, bg):
+    """the same operators, composed by torch autograd (each one is parity-tested on its own elsewhere)"""
+    from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from lsx_b200 import loss as L, render_utils as RU
+    P = raw["means3D"].shape[0]
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    pose = poses.detach().clone().requires_grad_(True)
+    m2s = []
+    for i, vw in enumerate(views):
+        xyz, rot = leaf["means3D"], leaf["rotations"]
+        if cfg.optimise_pose:
+            xyz, rot = RU.pose_transform(pose[vw.index], leaf["means3D"], leaf["rotations"])
+        scales, rots, opac, all_map = RU.gaussian_head(xyz, leaf["scales"], rot, leaf["opacity"], vw.viewmatrix, vw.campos)
+        s = GaussianRasterizationSettings(vw.H, vw.W, vw.tanfovx, vw.tanfovy, bg, 1.0, vw.viewmatrix, vw.projmatrix,
+                                          cfg.sh_degree, vw.campos, False, True, False, True)
+        m2 = torch.zeros(P, 3, device=DEV, requires_grad=True)
+        m2a = torch.zeros(P, 3, device=DEV, requires_grad=True)
+        color, lf, li, radii, obs, amap, depth = GaussianRasterizer(s)(
+            means3D=xyz, means2D=m2, means2D_abs=m2a, opacities=opac, shs=leaf["sh"].view(P, -1, 3),
+            language_feature_precomp=leaf["language_feature"], language_feature_instance_precomp=leaf["instance_feature"],
+            scales=scales, rotations=rots, all_map=all_map)
+        loss = L.image_loss(color, vw.gt_image, cfg.lambda_dssim)[0]
+        dn = RU.depth_to_normal(depth[0], vw.fx, vw.fy, vw.W * 0.5, vw.H * 0.5, alpha=amap[3])
+        loss = loss + cfg.normal_weight * (vw.image_weight * (dn - amap[:3]).abs().sum(0)).mean()
+        loss = loss + cfg.language_weight * L.masked_l1_loss(lf, vw.gt_language, vw.language_mask)
+        if cfg.cls3d:
+            loss = loss + L.loss_cls_3d(leaf["means3D"].detach(), leaf["language_feature"], cfg.reg3d_k, cfg.reg3d_lambda,
+                                        2_000_000, cfg.reg3d_samples, sample_indices=sample_idx[i])
+        loss.backward()
+        m2s.append((m2.grad, m2a.grad, radii, obs))
+    g = {k: v.grad for k, v in leaf.items()}
+    g["pose"] = pose.grad
+    return g, m2s
+
+
+@pytest.mark.parametrize("optimise_pose", [True, False])
+def test_hand_chained_backward_equals_autograd_composition(optimise_pose):
+    import bench_loop as bl
+    from lsx_b200.field_loop import FieldLoop, LoopConfig
+    raw, views, poses = _case()
+    P = raw["means3D"].shape[0]
+    cfg = LoopConfig(optimise_pose=optimise_pose)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    si = [bl.sample_indices(v.index, 0, P, cfg.reg3d_samples, DEV) for v in views]
+    loop = FieldLoop(raw, bl.LRS, bg, cfg, n_views=len(views), poses=poses)
+    losses = loop.gradient(views, si)
+    ref, m2s = _autograd_gradient(raw, views, poses, cfg, si, bg)
+    torch.cuda.synchronize()
+    assert set(losses) == {"l1", "ssim", "normal", "language", "cls3d"}
+    for name, v in loop.grads.views.items():
+        if name == "pose" and not optimise_pose:
+            continue
+        if name == "instance_feature":
+            assert float(v.abs().max()) == 0.0            # not supervised in this stage
+            continue
+        r = ref[name].reshape(v.shape)
+        assert float(r.abs().max()) > 0, name
+        assert _mixed(v, r) < 2e-4, (name, _mixed(v, r))
+    # densification statistics: the per-step delta merged into the persistent ones = the reference's per-view updates
+    from lsx_b200.multiview import DensifyStats
+    expect = DensifyStats.allocate(P, DEV)
+    for g2, g2a, radii, obs in m2s:
+        expect.add_view(g2, g2a, radii, obs)
+    assert _mixed(loop.stats.grad_accum, expect.grad_accum) < 2e-4
+    assert _mixed(loop.stats.grad_accum_abs, expect.grad_accum_abs) < 2e-4
+    assert torch.equal(loop.stats.denom, expect.denom) and torch.equal(loop.stats.max_radii2D, expect.max_radii2D)
+    # a second step must not re-count the first one (statistics are cumulative, the delta is per step)
+    loop.gradient(views, si)
+    assert torch.equal(loop.stats.denom, 2 * expect.denom)
+
+
+def test_steps_reduce_the_loss_and_keep_parameters_finite():
+    import bench_loop as bl
+    from lsx_b200.field_loop import FieldLoop, LoopConfig
+    raw, views, poses = _case(P=8_000, W=112, H=80)
+    cfg = LoopConfig()
+    loop = FieldLoop(raw, bl.LRS, torch.zeros(3, device=DEV), cfg, n_views=len(views), poses=poses)
+    si = [bl.sample_indices(v.index, 0, raw["means3D"].shape[0], cfg.reg3d_samples, DEV) for v in views]
+    total = lambda d: float(0.8 * d["l1"] + 0.2 * (len(views) - d["ssim"]) + d["language"])
+    first = total(loop.step(views, si))
+    for _ in range(30):
+        last = total(loop.step(views, si))
+    assert torch.isfinite(loop.params.flat).all()
+    assert last < first, (first, last)
+    assert not torch.equal(loop.params.views["pose"], poses)        # the camera rows are being optimised too
+
+
+def test_render_stats_against_brute_force():
+    """S = sum of n_contrib; B counted per (pixel, tile-list entry) with torch from the parsed scratch buffers."""
+    from lsx_b200 import ops
+    from lsx_b200.synthetic import make_camera, make_scene
+    P, W, H, F = 3_000, 96, 64, 3
+    scene = make_scene(P, W, H, F=F, seed=11).to(DEV)
+    cam = make_camera(W, H, yaw_deg=4.0).to(DEV)
+    fargs = hz.native_forward_args(scene, cam, torch.zeros(3, device=DEV), F)
+    fwd = dict(zip(hz.FWD_NAMES, ops.rasterize_gaussians(*fargs)))
+    R, Ct = fwd["num_rendered"], 3 + F + 3 + 5
+    st = ops.render_stats(R, fwd["geom"], fwd["binning"], fwd["img"], P, H, W, Ct)
+    buf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, R, W, H, Ct)
+    assert st["R"] == R and st["S"] == int(buf["n_contrib"].long().sum())
+    assert 0 < st["B"] <= 32 * st["Vb"] and st["Vb"] <= st["V"] <= st["L"] <= 8 * R
+    # brute force over (pixel, entry of its tile's list below n_contrib)
+    ranges, plist = buf["ranges"].long(), buf["point_list"].long()
+    co, m2 = buf["conic_opacity"], buf["means2D"]
+    gx = (W + 15) // 16
+    B = 0
+    ys, xs = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing="ij")
+    ncontrib = buf["n_contrib"].view(H, W).long()
+    for t in range(ranges.shape[0]):
+        a, b = int(ranges[t, 0]), int(ranges[t, 1])
+        if b <= a:
+            continue
+        tx, ty = t % gx, t // gx
+        sel = (xs // 16 == tx) & (ys // 16 == ty)
+        px, py, nc = xs[sel].float(), ys[sel].float(), ncontrib[sel]
+        ids = plist[a:b]
+        dx = m2[ids, 0][None, :] - px[:, None]
+        dy = m2[ids, 1][None, :] - py[:, None]
+        cx, cy, cz, op = co[ids, 0][None], co[ids, 1][None], co[ids, 2][None], co[ids, 3][None]
+        power = -0.5 * (cx * dx * dx + cz * dy * dy) - cy * dx * dy
+        alpha = torch.clamp(op * torch.exp(power), max=0.99)
+        pos = torch.arange(b - a, device=DEV)[None, :]
+        B += int(((pos < nc[:, None]) & (power <= 0) & (alpha >= 1.0 / 255.0)).sum())
+    assert abs(st["B"] - B) <= max(2, int(2e-5 * B)), (st["B"], B)     # a threshold flip of torch's expression order is allowed
+
+
+def test_module_gradient_sink_accumulates_views():
+    """GaussianRasterizer(settings, grad_buffers=arena views, accumulate=...) over two views: the arena holds the sum of the
+    two views' ordinary autograd gradients and the leaves get no .grad of their own for the sunk groups."""
+    from diff_LangSurf_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from lsx_b200.multiview import GradArena
+    from lsx_b200.synthetic import make_all_map, make_camera, make_scene, make_upstream_grads
+    P, W, H, F = 12_000, 176, 128, 16
+    scene = make_scene(P, W, H, F=F, seed=21).to(DEV)
+    g = make_upstream_grads(W, H, F, seed=22, device=DEV)
+    bg = torch.zeros(3, device=DEV)
+    cams = [make_camera(W, H, yaw_deg=y).to(DEV) for y in (-6.0, 7.0)]
+    arena = GradArena.allocate(P, 16, F, 3, DEV)
+
+    def run(sink):
+        leaf = lambda t: t.detach().clone().requires_grad_(True)
+        p = dict(m3=leaf(scene.means3D), sh=leaf(scene.shs), lf=leaf(scene.language_feature), li=leaf(scene.instance_feature),
+                 op=leaf(scene.opacities), sc=leaf(scene.scales), ro=leaf(scene.rotations))
+        for i, cam in enumerate(cams):
+            s = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.viewmatrix, cam.projmatrix, 3,
+                                              cam.campos, False, True, False, True)
+            rast = GaussianRasterizer(s, grad_buffers=arena.grad_buffers(), accumulate=i > 0) if sink else GaussianRasterizer(s)
+            m2 = torch.zeros(P, 3, device=DEV, requires_grad=True)
+            out = rast(means3D=p["m3"], means2D=m2, means2D_abs=m2, opacities=p["op"], shs=p["sh"],
+                       language_feature_precomp=p["lf"], language_feature_instance_precomp=p["li"], scales=p["sc"],
+                       rotations=p["ro"], all_map=make_all_map(scene, cam))
+            color, lf, li, _, _, amap, depth = out
+            torch.autograd.backward([color, lf, li, amap, depth], [g["color"], g["language_feature"], g["instance_feature"],
+                                                                   g["all_map"], g["plane_depth"]])
+        return p
+    plain = run(False)
+    sunk = run(True)
+    names = dict(m3="means3D", sh="sh", lf="language_feature", li="instance_feature", op="opacity", sc="scales", ro="rotations")
+    for k, gname in names.items():
+        assert sunk[k].grad is None, k
+        v = arena.views[gname]
+        assert hz.rel_err(v, plain[k].grad.reshape(v.shape)) < 2e-5, gname
+
+
+def test_mark_visible_matches_the_reference_export():
+    from lsx_b200 import ops
+    from lsx_b200.synthetic import make_camera, make_scene
+    ref = hz.load_ref("ref_rast_f3")
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for P, yaw in ((1, 0.0), (777, 10.0), (200_000, -12.0)):
+        scene = make_scene(P, 320, 240, seed=P).to(DEV)
+        cam = make_camera(320, 240, yaw_deg=yaw).to(DEV)
+        mine = ops.mark_visible(scene.means3D, cam.viewmatrix, cam.projmatrix)
+        theirs = ref.mark_visible(scene.means3D, cam.viewmatrix, cam.projmatrix)
+        assert mine.dtype == theirs.dtype == torch.bool and torch.equal(mine, theirs)
+        assert 0 < int(mine.sum()) < P or P == 1

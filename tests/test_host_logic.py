@@ -163,3 +163,43 @@ def test_oracle_small_properties():
     np.fill_diagonal(d2, np.inf)
     ref = np.sort(d2, axis=1)[:, :3].mean(1)
     assert np.allclose(orc.knn_mean_dist2(pts), ref, rtol=1e-5)
+
+
+def test_module_autograd_plumbing_with_a_stub_native_layer(monkeypatch):
+    """The nn.Module / autograd.Function layer on CPU tensors with the native `_C` functions stubbed out: argument counts,
+    the 7-tuple, which inputs receive gradients, and the multi-view gradient sink (sunk groups get None from autograd)."""
+    import types
+    import diff_LangSurf_rasterization as D
+    P, H, W = 5, 4, 4
+    seen = {}
+
+    def fwd(*a):
+        assert len(a) == 24
+        z = lambda *s: torch.zeros(*s)
+        return (3, z(3, H, W) + a[1].sum(), z(3, H, W) + a[3].sum(), z(3, H, W), torch.ones(P, dtype=torch.int32),
+                torch.ones(P, dtype=torch.int32), z(5, H, W) + a[10].sum(), z(1, H, W) + a[5].sum(), z(1), z(1), z(1))
+
+    def bwd(*a, grad_buffers=None, accumulate=False):
+        assert len(a) == 31
+        seen["sink"] = (grad_buffers, accumulate)
+        o = lambda *s: torch.ones(*s)
+        return (o(P, 3), o(P, 3), o(P, 3), o(P, 3), o(P, 3), o(P, 1), o(P, 3), o(P, 6), o(P, 16, 3), o(P, 3), o(P, 4), o(P, 5))
+
+    monkeypatch.setattr(D, "_C", types.SimpleNamespace(rasterize_gaussians=fwd, rasterize_gaussians_backward=bwd))
+    leaf = lambda *s: torch.randn(*s, requires_grad=True)
+    s = D.GaussianRasterizationSettings(H, W, 1., 1., torch.zeros(3), 1., torch.eye(4), torch.eye(4), 3, torch.zeros(3),
+                                        False, True, False, True)
+    for sink in (None, {"means3D": torch.zeros(P, 3), "sh": torch.zeros(P, 48), "opacity": torch.zeros(P, 1)}):
+        p = dict(m3=leaf(P, 3), sh=leaf(P, 16, 3), lf=leaf(P, 3), li=leaf(P, 3), op=leaf(P, 1), sc=leaf(P, 3), ro=leaf(P, 4),
+                 am=leaf(P, 5))
+        m2 = torch.zeros(P, 3, requires_grad=True)
+        out = D.GaussianRasterizer(s, grad_buffers=sink, accumulate=True)(
+            means3D=p["m3"], means2D=m2, means2D_abs=m2, opacities=p["op"], shs=p["sh"], language_feature_precomp=p["lf"],
+            language_feature_instance_precomp=p["li"], scales=p["sc"], rotations=p["ro"], all_map=p["am"])
+        assert len(out) == 7
+        (out[0].sum() + out[1].sum() + out[5].sum() + out[6].sum()).backward()
+        sunk = {"m3", "sh", "op"} if sink else set()
+        for k, v in p.items():
+            assert (v.grad is None) == (k in sunk), k
+        assert m2.grad is not None                      # screen-space gradients always reach autograd (densification)
+        assert (seen["sink"][0] is sink) and seen["sink"][1] == bool(sink)

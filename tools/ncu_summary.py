@@ -1,5 +1,9 @@
 """Summarise an .ncu-rep (ncu --set full) as a markdown table of the metrics DESIGN.md / bench.py quote.
-Usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-name regex] > profiles/x.md"""
+Usage: python tools/ncu_summary.py gpurun_out/x.ncu-rep [kernel-name regex] [--json profiles/ncu_render_kernels.json] > profiles/x.md
+
+--json also writes the record bench.py's `roofline.traffic` / `issue_slots_pct` are read from: per render kernel the dram bytes
+and issue-slot utilisation of this capture, stamped with the sha1 of the kernel sources in the tree (bench.py reports the
+record as stale, traffic = null, as soon as those sources change)."""
 import csv
 import io
 import subprocess
@@ -30,7 +34,43 @@ METRICS = [
 ]
 
 
+def _num(x):
+    return float(x.replace(",", ""))
+
+
+def write_json(path, rep, hdr, units, data):
+    import hashlib
+    import json
+    import os
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha1()
+    for name in ("render_fwd.cu", "render_bwd.cu", "tile_stage.cuh"):
+        with open(os.path.join(repo, "langscene-x_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rec = {"capture": os.path.basename(rep), "sources_sha1": h.hexdigest()}
+    for r in data:
+        kn = r[hdr.index("Kernel Name")]
+        key = "render_fwd" if "render_fwd_kernel" in kn else ("render_bwd" if "render_bwd_kernel" in kn else None)
+        if key is None or key in rec:
+            continue
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        rec[key] = {"kernel": kn.split("(")[0].replace("void ", ""),
+                    "dram_bytes": int(_num(r[ir]) * scale.get(units[ir], 1) + _num(r[iw]) * scale.get(units[iw], 1)),
+                    "issue_active_pct": _num(r[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]),
+                    "duration_ms_under_ncu": _num(r[hdr.index("gpu__time_duration.sum")]),
+                    "warp_instructions": _num(r[hdr.index("smsp__inst_executed.sum")]),
+                    "shared_wavefronts": _num(r[hdr.index("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")])}
+    with open(path, "w") as f:
+        json.dump(rec, f, indent=1)
+
+
 def main():
+    json_out = None
+    if "--json" in sys.argv:
+        i = sys.argv.index("--json")
+        json_out = sys.argv[i + 1]
+        del sys.argv[i:i + 2]
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -38,6 +78,8 @@ def main():
     if len(sys.argv) > 2:
         import re
         data = [r for r in data if re.search(sys.argv[2], r[hdr.index("Kernel Name")])]
+    if json_out:
+        write_json(json_out, rep, hdr, units, data)
     names = [r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")[-60:] for r in data]
     print(f"# ncu --set full summary of `{rep.split('/')[-1]}`\n")
     print("| metric | " + " | ".join(names) + " |")
