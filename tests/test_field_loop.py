@@ -74,8 +74,10 @@ def test_hand_chained_backward_equals_autograd_composition(optimise_pose):
     loop = FieldLoop(raw, bl.LRS, bg, cfg, n_views=len(views), poses=poses)
     losses = loop.gradient(views, si)
     ref, m2s = _autograd_gradient(raw, views, poses, cfg, si, bg)
+    ref2, _ = _autograd_gradient(raw, views, poses, cfg, si, bg)
     torch.cuda.synchronize()
     assert set(losses) == {"l1", "ssim", "normal", "language", "cls3d"}
+    report = {}
     for name, v in loop.grads.views.items():
         if name == "pose" and not optimise_pose:
             continue
@@ -84,7 +86,19 @@ def test_hand_chained_backward_equals_autograd_composition(optimise_pose):
             continue
         r = ref[name].reshape(v.shape)
         assert float(r.abs().max()) > 0, name
-        assert _mixed(v, r) < 2e-4, (name, _mixed(v, r))
+        # Both sides run the same kernels; what differs is the order of the fp32 atomics of the tile backward pass (different
+        # from run to run) and of the view accumulation.  The conic -> covariance -> position / scale / rotation chain
+        # amplifies that noise where its terms cancel (backward.cu:210-212,333-336), heavy-tailed over the elements, so every
+        # bound is relative to the autograd composition's OWN run-to-run spread in the same statistic: rms error (robust),
+        # element-wise maximum (loose factor: a maximum over 10^4..10^6 heavy-tailed samples), tensor-scale maximum
+        # (BASELINE.json's gradient tolerance).  A chaining error (missing term, wrong sign, wrong buffer) is O(1) in all.
+        r2 = ref2[name].reshape(v.shape)
+        rms = lambda a, b: float((a.double() - b.double()).pow(2).mean().sqrt() / b.double().pow(2).mean().sqrt())
+        report[name] = dict(rms=(rms(v, r), rms(r2, r)), mixed=(_mixed(v, r), _mixed(r2, r)), scale=(hz.rel_err(v, r), hz.rel_err(r2, r)))
+        assert rms(v, r) < max(2e-5, 4.0 * rms(r2, r)), (name, report[name])
+        assert _mixed(v, r) < max(2e-4, 20.0 * _mixed(r2, r)), (name, report[name])
+        assert hz.rel_err(v, r) < max(1e-4, 6.0 * hz.rel_err(r2, r)), (name, report[name])
+    print("field loop vs autograd composition, (error, self spread of the composition):", report)
     # densification statistics: the per-step delta merged into the persistent ones = the reference's per-view updates
     from lsx_b200.multiview import DensifyStats
     expect = DensifyStats.allocate(P, DEV)
