@@ -69,3 +69,31 @@ def build_library(force=False, verbose=False):
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+
+
+ROUTE_B_SRC = os.path.join(ROOT, "integration", "rasterize_points_lsx.cpp")
+ROUTE_B_LIB = os.path.join(ROOT, "integration", "lsx_route_b.so")
+
+
+def build_route_b(force=False):
+    """INTEGRATION.md Route B as a binary: the reference's own C++ glue (pybind `_C` functions with the reference's signatures)
+    re-bound on the C ABI, compiled with g++ against torch's headers and linked with liblsx_b200.so.  It proves that the stub
+    the integration guide shows compiles and binds; tests/test_route_b.py runs it next to the ctypes route on the GPU."""
+    import sysconfig
+    import torch
+    from torch.utils import cpp_extension as ce
+    build_library()
+    if not force and not _stale(ROUTE_B_LIB, [ROUTE_B_SRC, LIB_PATH, os.path.join(REPO, "include", "lsx_rasterizer.h")]):
+        return ROUTE_B_LIB
+    inc = ce.include_paths("cuda") + [sysconfig.get_paths()["include"], os.path.join(REPO, "include")]
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", ROUTE_B_SRC, "-o", ROUTE_B_LIB,
+           *[f"-I{p}" for p in inc], f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-DTORCH_EXTENSION_NAME=lsx_route_b",
+           f"-L{PKG_DIR}", "-l:liblsx_b200.so", f"-Wl,-rpath,{PKG_DIR}", "-Wl,-rpath,$ORIGIN/../lsx_b200"]
+    for p in ce.library_paths("cuda"):
+        cmd += [f"-L{p}", f"-Wl,-rpath,{p}"]
+    cmd += ["-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"Route B glue failed to build:\n{r.stderr[-6000:]}")
+    return ROUTE_B_LIB
