@@ -189,6 +189,32 @@ def time_loop(step_fn, steps, warmup, world, detail=None):
     return float(ms.item())
 
 
+def time_collective(flat, world, reps=10):
+    """The arena all-reduce alone (no compute around it), CUDA events, max over ranks: what the step pays when nothing
+    overlaps it.  busbw = algbw * 2 (N - 1) / N, NCCL's convention."""
+    if world <= 1:
+        return None
+    buf = torch.empty_like(flat)
+    for _ in range(3):
+        dist.all_reduce(buf)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dist.all_reduce(buf)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=flat.device)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    nbytes = flat.numel() * 4
+    alg = nbytes / (ms * 1e-3) / 1e9
+    return {"what": "ncclAllReduce(sum, fp32) of the flat gradient arena, back to back, nothing else on the GPU", "bytes": nbytes,
+            "ms": ms, "algbw_GBs": alg, "busbw_GBs": alg * 2 * (world - 1) / world}
+
+
 def native_stepper(mod, fargs, grads, arena=None, world=1):
     """Single-view device-resident step (tools/): raw `_C`-level forward + backward."""
     import harness as hz
@@ -498,6 +524,7 @@ def main():
         estep, h2d, d2h = e2e_stepper(mod, views, grads, arena, world)
     ms_e2e = time_loop(estep, args.steps, max(3, warmup // 2), world) / args.steps
     clocks = sampler.stop() if sampler else None
+    collective = time_collective(arena.flat, world)
     e2e = {"value": world * V * W * H / (ms_e2e * 1e-3) / 1e6, "unit": "MPix/s", "ms_per_step": ms_e2e,
            "ms_per_iter": ms_e2e / V, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "api": "diff_LangSurf_rasterization.GaussianRasterizer + autograd" if new
@@ -528,7 +555,7 @@ def main():
                    "views_per_gpu": V, "ms_per_iter_is": "ms_per_step / views_per_gpu = one single-view fwd+bwd (BASELINE's ms/iter)",
                    "l2": "per-view working set (~1.6 GB of inputs, records, lists, images, gradients) exceeds the 126 MB L2; no flush needed",
                    "upstream_grads": "fixed N(0,1)/(W*H) tensors, no loss inside the timed region"},
-        "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "collective": collective,
         "stats": {"P_vis": P_vis, "R": R, "S": S, "B": stats_views[0].get("B"), "Ct": Ct, "per_view": stats_views,
                   "what": "S = (pixel, entry) tests per render pass of the reference's loops = sum of n_contrib; B = (pixel, entry) "
                           "blends; V = (8x4 block, entry) visits of this library's backward; Vb = visits in which a pixel blends; "

@@ -367,7 +367,6 @@ def run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler):
 
     def e2e_step():
         feeder.fetch(0)
-        staged = []
         if new:
             # FieldLoop.step wants the views up front; stage them one ahead of the compute through the two slots
             def gen():
@@ -393,10 +392,14 @@ def run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler):
             loop.opt.step()
             loop.cam_opt.step()
             out = {"loss": tot}
-        del staged
         return torch.stack(list(out.values())).to("cpu")
     ms_e2e = time_loop(e2e_step, args.steps, 3, world) / args.steps
     clocks = sampler.stop() if sampler else None
+    collective = None
+    if world > 1:
+        import bench
+        collective = bench.time_collective(loop.grads.flat if new else torch.empty(sum(t.numel() for t in loop.p.values()), device=device),
+                                           world)
 
     # ---- distCUDA2 (config 5: "distCUDA2 initialisation included"): timed once per run, reported separately ----
     knn = None
@@ -442,7 +445,7 @@ def run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler):
         "e2e": {"value": world * V / (ms_e2e * 1e-3), "unit": "views/s", "ms_per_step": ms_e2e, "ms_per_view": ms_e2e / V,
                 "h2d_bytes_per_step": feeder.bytes_per_step, "d2h_bytes_per_step": 4 * (5 if new else 1),
                 "api": "lsx_b200.field_loop.FieldLoop.step" if new else "reference-style torch loop around the reference _C module"},
-        "gpu_launches": launches, "clocks": clocks,
+        "gpu_launches": launches, "clocks": clocks, "collective": collective,
     }
     if parity is not None:
         out["parity"] = parity

@@ -144,6 +144,7 @@ class FieldLoop:
         self._g_one = torch.tensor([1.0], device=dev)
         self._empty = torch.Tensor([])
         self._zero_img: Dict[tuple, torch.Tensor] = {}
+        self.debug_tap = None
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
 
@@ -228,6 +229,10 @@ class FieldLoop:
                                                pv["sh"].view(P, self.M, 3), cfg.sh_degree, view.campos, geom, R, binning, img,
                                                True, False, True, grad_buffers=sink, accumulate=acc)
         (g_m2d, g_m2d_abs, _gc, _gl, _gi, g_opac, g_m3d, _gcov, _gsh, g_scales, g_rot, g_allmap) = bwd
+        if self.debug_tap is not None:      # tests / tools: the intermediates of this view, cloned
+            self.debug_tap.append({k: v.detach().clone() for k, v in dict(
+                color=color, lang=lang, amap=amap, depth=depth, g_color=g_color, g_lang=g_lang, g_amap=g_amap, g_depth=g_depth,
+                g_m3d=g_m3d, g_scales=g_scales, g_rot=g_rot, g_opac=g_opac, g_allmap=g_allmap, g_m2d=g_m2d).items()})
 
         # -- 3-D neighbourhood regulariser on the language feature parameter (adds into the arena) --
         if cfg.cls3d and sample_idx is not None:
