@@ -415,7 +415,8 @@ def main():
     ap.add_argument("--views-per-gpu", type=int, default=None,
                     help="views rendered by every GPU per step (default 8: 8 x 8 GPUs = the 64-view batch of BASELINE config 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="loop configs: one blocking all-reduce instead of per-group async ones")
+    ap.add_argument("--overlap", action="store_true", help="loop configs: per-group async all-reduces under the last view's backward "
+                                                         "instead of one blocking collective (measured slower at N = 2)")
     ap.add_argument("--no-parity", action="store_true", help="loop configs, N > 1: skip the untimed all-reduce parity check")
     ap.add_argument("--knn", action="store_true", help="loop configs: also time distCUDA2 over the scene's points")
     args = ap.parse_args()

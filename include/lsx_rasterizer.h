@@ -92,6 +92,13 @@ typedef struct lsx_forward_args {
     lsx_alloc_fn binning_alloc; void* binning_user;
     lsx_alloc_fn image_alloc;   void* image_user;
     void* stream;
+    /* ABI v5 — speculative binning capacity (0 = off).  The list length num_rendered is only known on the device after the
+     * duplicate-offset scan; the reference reads it back in the middle of the forward pass and lets the stream drain
+     * (rasterizer_impl.cu:291).  With a hint > 0 (e.g. 1.25 x the previous call's num_rendered for this scene) the library
+     * sizes the binning scratch and every kernel behind the scan for that capacity, enqueues them at once and only then
+     * waits for the (long finished) scan: the stream never drains.  If the hint turns out too small, binning and render are
+     * repeated with the exact size before the call returns — outputs and *num_rendered are always those of the exact path. */
+    int32_t binning_capacity_hint;
 } lsx_forward_args;
 
 /* Returns 0 and stores the number of (Gaussian,tile) duplicates in *num_rendered.
@@ -149,6 +156,9 @@ typedef struct lsx_backward_args {
      * (which must then be initialised) instead of overwriting it; 0 = overwrite everything.  The per-view screen-space
      * outputs dL_dmeans2D, dL_dmeans2D_abs and dL_dconic are always overwritten.  (ABI v5: was a boolean for all groups.) */
     int32_t accumulate_param_grads;
+    /* ABI v5: size in bytes of the binning buffer the forward call allocated through binning_alloc (its list capacity is
+     * recovered from it); 0 = the forward call ran without a capacity hint (capacity = R rounded up to 64). */
+    uint64_t binning_bytes;
 } lsx_backward_args;
 
 #define LSX_ACC_MEANS3D 0x001
@@ -418,8 +428,12 @@ LSX_API int lsx_scratch_layout_query(int32_t P, int32_t W, int32_t H, int32_t R,
 /* Materialise the sorted 64-bit keys (tile << 32 | depth bits) the reference keeps in
  * BinningState::point_list_keys (rasterizer_impl.cu:102-106), from this library's scratch. */
 LSX_API int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels,
-                          const char* geom_buffer, const char* binning_buffer, const char* image_buffer,
-                          uint64_t* keys_out, void* stream);
+                          const char* geom_buffer, const char* binning_buffer, size_t binning_bytes,
+                          const char* image_buffer, uint64_t* keys_out, void* stream);
+
+/* List capacity (a multiple of 64, >= num_rendered) of a binning buffer of `binning_bytes` bytes allocated by a forward call at
+ * this image size, or -1 if no capacity has that size.  lsx_scratch_layout_query takes this value as its R. */
+LSX_API int32_t lsx_binning_capacity(size_t binning_bytes, int32_t W, int32_t H);
 
 /* Workload counters of one rendered view, counted on the device from the scratch of a forward call (S, B, R
  * accompany every number).  stats_out: DEVICE array of 8 uint64, written as
@@ -428,7 +442,8 @@ LSX_API int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, in
  *   [2] V   (8x4 block, entry) visits of this library's backward pass      [3] Vb  visits in which some pixel blends
  *   [4] L   total length of the per-block compacted lists                  [5..7] reserved (0) */
 LSX_API int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
-                     const char* binning_buffer, const char* image_buffer, uint64_t* stats_out, void* stream);
+                     const char* binning_buffer, size_t binning_bytes, const char* image_buffer, uint64_t* stats_out,
+                     void* stream);
 
 /* number of kernels launched by this library since process start (bench.py "gpu_launches") */
 LSX_API uint64_t lsx_kernel_launch_count(void);

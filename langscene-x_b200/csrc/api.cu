@@ -210,6 +210,53 @@ int bits_for(uint32_t n) {
     return b;
 }
 
+// ---- binning capacity ------------------------------------------------------------------------------------------
+// The binning scratch is carved for a CAPACITY of list slots, a multiple of 64: num_rendered rounded up, or the
+// caller's speculative hint.  The backward pass (and the debug / statistics helpers) recover the capacity from the
+// size of the binning buffer, which is strictly increasing over multiples of 64.
+int round_up64(long long r) { return (int)((r + 63) / 64 * 64); }
+
+int capacity_from_bytes(size_t bytes, int num_tiles) {
+    long long lo = 0, hi = (0x7fffffffll / 64);  // capacity = 64 * x
+    while (lo < hi) {
+        const long long mid = (lo + hi + 1) / 2;
+        if (carve_binning(nullptr, (int)(mid * 64), num_tiles, nullptr).bytes <= bytes) lo = mid; else hi = mid - 1;
+    }
+    const int cap = (int)(lo * 64);
+    return carve_binning(nullptr, cap, num_tiles, nullptr).bytes == bytes ? cap : -1;
+}
+
+// pinned word + event for the asynchronous read of num_rendered in speculative mode (host-side pool, no device state)
+struct HostSlot {
+    uint32_t* word = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+std::mutex g_slot_mu;
+std::vector<HostSlot> g_slots;
+
+bool acquire_slot(HostSlot* out) {
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mu);
+        if (!g_slots.empty()) {
+            *out = g_slots.back();
+            g_slots.pop_back();
+            return true;
+        }
+    }
+    HostSlot s;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&s.word), 64, cudaHostAllocDefault) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaFreeHost(s.word);
+        return false;
+    }
+    *out = s;
+    return true;
+}
+void release_slot(const HostSlot& s) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    g_slots.push_back(s);
+}
+
 int blend_channels(int include_feature, int render_geo, int F, int Fi) {
     return 3 + (include_feature ? F + Fi : 0) + (render_geo ? 5 : 0);
 }
@@ -360,86 +407,123 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     if (rc) return rc;
     const uint32_t* order = gm.order[order_buf];
 
-    // ---- K2: duplicate offsets in depth order, total -> host ------------------------------------
-    uint32_t R_host = 0;
+    // ---- K2: duplicate offsets in depth order; the total (num_rendered) stays on the device ------
     {
         StageTimer _t(LSX_STAGE_OFFSETS_SCAN, stream);
         rc = exclusive_scan_u32(gm.tiles_touched, order, gm.offsets, P, gm.total, gm.scan_temp, stream, debug);
         if (rc) return rc;
-        LSX_CUDA_OK(cudaMemcpyAsync(&R_host, gm.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     }
-    LSX_CUDA_OK(cudaStreamSynchronize(stream));
-    if (R_host > 0x7fffffffu) {
-        set_error("lsx_rasterize_forward: %u duplicated splats overflow the 31-bit list index", R_host);
-        return -5;
-    }
-    const int R = (int)R_host;
 
-    BinningScratch bn = carve_binning(nullptr, R, num_tiles, nullptr);
-    char* bbase = a->binning_alloc(a->binning_user, bn.bytes);
-    if (!bbase) {
-        set_error("lsx_rasterize_forward: binning scratch allocation failed");
-        return -4;
-    }
-    bn = carve_binning(bbase, R, num_tiles, nullptr);
-
-    // ---- K3/K4/K5: emit (tile, idx) pairs in depth order, stable tile sort, tile ranges -----------
+    // ---- K3..K6 for a given list capacity: emit (tile, idx) pairs in depth order, stable tile sort, tile ranges,
+    //      footprint masks + per-block lists, tile render.  Every kernel is sized by `cap`, never by num_rendered. ----
     const int tile_bits = bits_for((uint32_t)num_tiles);
     const int passes = radix_sort_num_passes(0, tile_bits);
-    uint32_t* vals[2];
-    vals[passes & 1] = bn.point_list;  // so that the sorted values end in point_list
-    vals[(passes & 1) ^ 1] = bn.vals_alt;
-    if (R > 0) {
-        {
-            StageTimer _t(LSX_STAGE_EMIT, stream);
-            rc = launch_emit_tile_pairs(P, order, gm.offsets, gm.means2D, a->radii, grid_x, grid_y, bn.tile_keys[0],
-                                        vals[0], stream, debug);
+    auto bin_and_render = [&](const int cap) -> int {
+        BinningScratch bn = carve_binning(nullptr, cap, num_tiles, nullptr);
+        char* bbase = a->binning_alloc(a->binning_user, bn.bytes);
+        if (!bbase) {
+            set_error("lsx_rasterize_forward: binning scratch allocation failed");
+            return -4;
         }
-        if (rc) return rc;
-        int res = 0;
-        {
-            StageTimer _t(LSX_STAGE_TILE_SORT, stream);
-            rc = radix_sort_pairs_u32(bn.tile_keys, vals, R, 0, tile_bits, false, bn.sort_temp, &res, stream, debug);
+        bn = carve_binning(bbase, cap, num_tiles, nullptr);
+        uint32_t* vals[2];
+        vals[passes & 1] = bn.point_list;  // so that the sorted values end in point_list
+        vals[(passes & 1) ^ 1] = bn.vals_alt;
+        int r2 = 0;
+        if (cap > 0) {
+            {
+                StageTimer _t(LSX_STAGE_EMIT, stream);
+                r2 = launch_emit_tile_pairs(P, order, gm.offsets, gm.means2D, a->radii, grid_x, grid_y, bn.tile_keys[0], vals[0],
+                                            (uint32_t)cap, gm.total, stream, debug);
+            }
+            if (r2) return r2;
+            int res = 0;
+            {
+                StageTimer _t(LSX_STAGE_TILE_SORT, stream);
+                r2 = radix_sort_pairs_u32(bn.tile_keys, vals, cap, 0, tile_bits, false, bn.sort_temp, &res, stream, debug);
+            }
+            if (r2) return r2;
+            {
+                StageTimer _t(LSX_STAGE_TILE_RANGES, stream);
+                r2 = launch_tile_ranges(cap, bn.tile_keys[res], im.ranges, num_tiles, stream, debug);
+            }
+            if (r2) return r2;
+            {
+                StageTimer _t(LSX_STAGE_FOOTPRINT_MASKS, stream);
+                r2 = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, bn.blk_list,
+                                            (size_t)cap, bn.blk_cnt, stream, debug);
+            }
+            if (r2) return r2;
+        } else {
+            r2 = launch_tile_ranges(0, nullptr, im.ranges, num_tiles, stream, debug);
+            if (r2) return r2;
         }
-        if (rc) return rc;
+        RenderParams rp{};
+        rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
+        rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
+        rp.n_channels = nch; rp.rec_stride = rs;
+        rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
+        rp.blk_list = bn.blk_list; rp.list_stride = (size_t)cap; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
+        rp.bg = a->background;
+        rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
+        rp.out_color = a->out_color; rp.out_language_feature = a->out_language_feature;
+        rp.out_language_feature_instance = a->out_language_feature_instance; rp.out_observe = a->out_observe;
+        rp.out_all_map = a->out_all_map; rp.out_plane_depth = a->out_plane_depth;
         {
-            StageTimer _t(LSX_STAGE_TILE_RANGES, stream);
-            rc = launch_tile_ranges(R, bn.tile_keys[res], im.ranges, num_tiles, stream, debug);
+            StageTimer _t(LSX_STAGE_RENDER_FWD, stream);
+            r2 = launch_render_fwd(rp, stream, debug);
         }
-        if (rc) return rc;
-        {
-            StageTimer _t(LSX_STAGE_FOOTPRINT_MASKS, stream);
-            rc = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, bn.blk_list,
-                                        (size_t)R, bn.blk_cnt, stream, debug);
+        if (r2) return r2;
+        if (!a->render_geo) {
+            LSX_CUDA_OK(cudaMemsetAsync(a->out_all_map, 0, 5 * HW * sizeof(float), stream));
+            LSX_CUDA_OK(cudaMemsetAsync(a->out_plane_depth, 0, HW * sizeof(float), stream));
         }
-        if (rc) return rc;
-    } else {
-        rc = launch_tile_ranges(0, nullptr, im.ranges, num_tiles, stream, debug);
-        if (rc) return rc;
-    }
+        return 0;
+    };
 
-    // ---- K6: tile render ----------------------------------------------------------------------------
-    RenderParams rp{};
-    rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
-    rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
-    rp.n_channels = nch; rp.rec_stride = rs;
-    rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
-    rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
-    rp.bg = a->background;
-    rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
-    rp.out_color = a->out_color; rp.out_language_feature = a->out_language_feature;
-    rp.out_language_feature_instance = a->out_language_feature_instance; rp.out_observe = a->out_observe;
-    rp.out_all_map = a->out_all_map; rp.out_plane_depth = a->out_plane_depth;
-    {
-        StageTimer _t(LSX_STAGE_RENDER_FWD, stream);
-        rc = launch_render_fwd(rp, stream, debug);
+    uint32_t R_host = 0;
+    if (a->binning_capacity_hint > 0 && !debug) {
+        // Speculative: everything behind the scan is enqueued for the hinted capacity BEFORE the host knows
+        // num_rendered; the host then waits only for the event behind the scan (the GPU is already busy with the
+        // kernels behind it), so the stream never drains in the middle of a forward call.  If the hint was too
+        // small the binning + render are repeated with the exact capacity: results are always those of the exact path.
+        HostSlot slot;
+        if (!acquire_slot(&slot)) {
+            set_error("lsx_rasterize_forward: could not allocate the pinned result word");
+            return -2;
+        }
+        LSX_CUDA_OK(cudaMemcpyAsync(slot.word, gm.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        LSX_CUDA_OK(cudaEventRecord(slot.ev, stream));
+        const int cap = round_up64(a->binning_capacity_hint);
+        rc = bin_and_render(cap);
+        const cudaError_t ee = cudaEventSynchronize(slot.ev);
+        R_host = *slot.word;
+        release_slot(slot);
+        if (rc) return rc;
+        if (ee != cudaSuccess) {
+            set_error("lsx_rasterize_forward: waiting for num_rendered failed: %s", cudaGetErrorString(ee));
+            return -2;
+        }
+        if (R_host > 0x7fffffffu - 64u) {
+            set_error("lsx_rasterize_forward: %u duplicated splats overflow the 31-bit list index", R_host);
+            return -5;
+        }
+        if (R_host > (uint32_t)cap) {  // hint too small: redo with the exact size (out_observe was counted into)
+            LSX_CUDA_OK(cudaMemsetAsync(a->out_observe, 0, (size_t)P * sizeof(int), stream));
+            rc = bin_and_render(round_up64(R_host));
+            if (rc) return rc;
+        }
+    } else {
+        LSX_CUDA_OK(cudaMemcpyAsync(&R_host, gm.total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        LSX_CUDA_OK(cudaStreamSynchronize(stream));
+        if (R_host > 0x7fffffffu - 64u) {
+            set_error("lsx_rasterize_forward: %u duplicated splats overflow the 31-bit list index", R_host);
+            return -5;
+        }
+        rc = bin_and_render(round_up64(R_host));
+        if (rc) return rc;
     }
-    if (rc) return rc;
-    if (!a->render_geo) {
-        LSX_CUDA_OK(cudaMemsetAsync(a->out_all_map, 0, 5 * HW * sizeof(float), stream));
-        LSX_CUDA_OK(cudaMemsetAsync(a->out_plane_depth, 0, HW * sizeof(float), stream));
-    }
-    *num_rendered = R;
+    *num_rendered = (int)R_host;
     return 0;
 }
 
@@ -478,7 +562,16 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     const int rs = record_stride(nch);
     GeomScratch gm = carve_geom(const_cast<char*>(a->geom_buffer), P, rs);
     ImageScratch im = carve_image(const_cast<char*>(a->image_buffer), W, H, nullptr);
-    BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), R, (int)(grid_x * grid_y), nullptr);
+    int cap = round_up64(R);
+    if (a->binning_bytes != 0) {
+        cap = capacity_from_bytes((size_t)a->binning_bytes, (int)(grid_x * grid_y));
+        if (cap < R) {
+            set_error("lsx_rasterize_backward: binning buffer of %llu bytes does not belong to a forward call of this size",
+                      (unsigned long long)a->binning_bytes);
+            return -1;
+        }
+    }
+    BinningScratch bn = carve_binning(const_cast<char*>(a->binning_buffer), cap, (int)(grid_x * grid_y), nullptr);
 
     const int gs = round_up4(nch) + 8;  // floats per packed gradient record
     {
@@ -493,7 +586,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
         rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
         rp.n_channels = nch; rp.rec_stride = rs;
         rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
-        rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
+        rp.blk_list = bn.blk_list; rp.list_stride = (size_t)cap; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
         rp.bg = a->background;
         rp.final_T = im.final_T; rp.n_contrib = im.n_contrib;
         rp.dL_dout_color = a->dL_dout_color; rp.dL_dout_language_feature = a->dL_dout_language_feature;
@@ -554,8 +647,14 @@ int lsx_knn_mean_dist2(int32_t P, const float* points, float* out, lsx_alloc_fn 
     return knn_mean_dist2(P, points, out, temp, static_cast<cudaStream_t>(stream));
 }
 
+int32_t lsx_binning_capacity(size_t binning_bytes, int32_t W, int32_t H) {
+    if (W <= 0 || H <= 0) return -1;
+    return capacity_from_bytes(binning_bytes, ceil_div(W, TILE_X) * ceil_div(H, TILE_Y));
+}
+
 int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
-                          const char* binning_buffer, const char* image_buffer, uint64_t* keys_out, void* stream) {
+                          const char* binning_buffer, size_t binning_bytes, const char* image_buffer, uint64_t* keys_out,
+                          void* stream) {
     if (P <= 0 || R <= 0 || !geom_buffer || !binning_buffer || !image_buffer || !keys_out) {
         set_error("lsx_debug_sorted_keys: bad arguments");
         return -1;
@@ -563,12 +662,18 @@ int lsx_debug_sorted_keys(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_
     GeomScratch gm = carve_geom(const_cast<char*>(geom_buffer), P, record_stride(n_blend_channels));
     ImageScratch im = carve_image(const_cast<char*>(image_buffer), W, H, nullptr);
     const int tiles = ceil_div(W, TILE_X) * ceil_div(H, TILE_Y);
-    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), R, tiles, nullptr);
+    const int cap = binning_bytes ? capacity_from_bytes(binning_bytes, tiles) : round_up64(R);
+    if (cap < R) {
+        set_error("lsx_debug_sorted_keys: binning buffer size does not match");
+        return -1;
+    }
+    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), cap, tiles, nullptr);
     return launch_debug_keys(tiles, im.ranges, bn.point_list, gm.depths, keys_out, static_cast<cudaStream_t>(stream));
 }
 
 int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
-                     const char* binning_buffer, const char* image_buffer, uint64_t* stats_out, void* stream) {
+                     const char* binning_buffer, size_t binning_bytes, const char* image_buffer, uint64_t* stats_out,
+                     void* stream) {
     if (P < 0 || W <= 0 || H <= 0 || R < 0 || !stats_out || n_blend_channels < 3 || n_blend_channels > LSX_MAX_BLEND_CHANNELS ||
         (P > 0 && (!geom_buffer || !image_buffer)) || (R > 0 && !binning_buffer)) {
         set_error("lsx_render_stats: bad arguments");
@@ -583,11 +688,16 @@ int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend
     GeomScratch gm = carve_geom(const_cast<char*>(geom_buffer), P, rs);
     ImageScratch im = carve_image(const_cast<char*>(image_buffer), W, H, nullptr);
     const uint32_t grid_x = (uint32_t)ceil_div(W, TILE_X), grid_y = (uint32_t)ceil_div(H, TILE_Y);
-    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), R, (int)(grid_x * grid_y), nullptr);
+    const int cap = binning_bytes ? capacity_from_bytes(binning_bytes, (int)(grid_x * grid_y)) : round_up64(R);
+    if (cap < R) {
+        set_error("lsx_render_stats: binning buffer size does not match");
+        return -1;
+    }
+    BinningScratch bn = carve_binning(const_cast<char*>(binning_buffer), cap, (int)(grid_x * grid_y), nullptr);
     RenderParams rp{};
     rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.n_channels = n_blend_channels; rp.rec_stride = rs;
     rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.records = gm.records;
-    rp.blk_list = bn.blk_list; rp.list_stride = (size_t)R; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
+    rp.blk_list = bn.blk_list; rp.list_stride = (size_t)cap; rp.blk_cnt = bn.blk_cnt; rp.k_contrib = im.k_contrib;
     rp.n_contrib = im.n_contrib;
     return launch_render_stats(rp, reinterpret_cast<unsigned long long*>(stats_out), st);
 }

@@ -23,11 +23,23 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
                                                               const float2* __restrict__ means2D,
                                                               const int* __restrict__ radii, uint32_t grid_x,
                                                               uint32_t grid_y, uint32_t* __restrict__ tile_keys,
-                                                              uint32_t* __restrict__ vals) {
+                                                              uint32_t* __restrict__ vals, const uint32_t cap,
+                                                              const uint32_t* __restrict__ total_pairs) {
     constexpr unsigned kFull = 0xffffffffu;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const int k0 = k - (int)lane;  // warp-uniform
+    // The output arrays hold `cap` >= R slots (R rounded up to 64, or a speculative capacity chosen before R was known on
+    // the host): slots R .. cap-1 get the key 0xffffffff, which sorts behind every tile id on any digit range, and are
+    // never referenced by a tile range.  If R > cap (speculation too small) the surplus pairs are dropped here and the
+    // host, which learns R a little later, repeats the binning with the exact size.
+    {
+        const uint32_t R = __ldg(total_pairs);
+        for (uint32_t i = R + (uint32_t)k; i < cap; i += gridDim.x * blockDim.x) {
+            tile_keys[i] = 0xffffffffu;
+            vals[i] = 0u;
+        }
+    }
     if (k0 >= P) return;
     uint32_t g = 0, w = 0, count = 0;
     uint2 rmin = make_uint2(0u, 0u), rmax;
@@ -63,7 +75,7 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
         const uint32_t sx = __shfl_sync(kFull, rmin.x, (int)s);
         const uint32_t sy = __shfl_sync(kFull, rmin.y, (int)s);
         const uint32_t sp = __shfl_sync(kFull, pre, (int)s);
-        if (j < total) {
+        if (j < total && base + j < cap) {
             const uint32_t t = j - sp;
             const uint32_t row = t / sw, col = t - row * sw;  // row-major over the rectangle, y outer (duplicateWithKeys)
             tile_keys[base + j] = (sy + row) * grid_x + (sx + col);
@@ -73,8 +85,9 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
 }
 
 // four consecutive keys per thread (one 16-B load + the preceding key)
+// R = number of slots (real pairs followed by 0xffffffff padding keys, which belong to no tile)
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys,
-                                                          uint2* __restrict__ ranges) {
+                                                          uint2* __restrict__ ranges, const uint32_t num_tiles) {
     const long long base = 4ll * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
     if (base >= R) return;
     uint32_t k[4];
@@ -92,12 +105,12 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t*
         if (i < R) {
             const uint32_t t = k[j];
             if (i == 0) {
-                ranges[t].x = 0;
+                if (t < num_tiles) ranges[t].x = 0;
             } else if (prev != t) {
-                ranges[prev].y = (uint32_t)i;
-                ranges[t].x = (uint32_t)i;
+                if (prev < num_tiles) ranges[prev].y = (uint32_t)i;
+                if (t < num_tiles) ranges[t].x = (uint32_t)i;
             }
-            if (i == R - 1) ranges[t].y = (uint32_t)R;
+            if (i == R - 1 && t < num_tiles) ranges[t].y = (uint32_t)R;
             prev = t;
         }
     }
@@ -118,10 +131,10 @@ __global__ void __launch_bounds__(256) debug_keys_kernel(int num_tiles, const ui
 
 int launch_emit_tile_pairs(int P, const uint32_t* sorted_idx, const uint32_t* offsets, const float2* means2D,
                            const int* radii, uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* vals,
-                           cudaStream_t stream, bool debug) {
+                           uint32_t capacity, const uint32_t* total_pairs, cudaStream_t stream, bool debug) {
     if (P <= 0) return 0;
     emit_tile_pairs_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, sorted_idx, offsets, means2D, radii, grid_x, grid_y,
-                                                                 tile_keys, vals);
+                                                                 tile_keys, vals, capacity, total_pairs);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
@@ -130,7 +143,7 @@ int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, i
                        bool debug) {
     LSX_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
     if (R <= 0) return 0;
-    tile_ranges_kernel<<<ceil_div(ceil_div(R, 4), 256), 256, 0, stream>>>(R, sorted_tile_keys, ranges);
+    tile_ranges_kernel<<<ceil_div(ceil_div(R, 4), 256), 256, 0, stream>>>(R, sorted_tile_keys, ranges, (uint32_t)num_tiles);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

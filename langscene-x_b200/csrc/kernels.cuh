@@ -103,7 +103,8 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out
 // ---- binning (binning.cu) ---------------------------------------------------------------------
 int launch_emit_tile_pairs(int P, const uint32_t* sorted_idx, const uint32_t* offsets, const float2* means2D,
                            const int* radii, uint32_t grid_x, uint32_t grid_y, uint32_t* tile_keys, uint32_t* vals,
-                           cudaStream_t stream, bool debug);
+                           uint32_t capacity, const uint32_t* total_pairs, cudaStream_t stream, bool debug);
+// R = slots of the key array (pairs + 0xffffffff padding)
 int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, int num_tiles, cudaStream_t stream,
                        bool debug);
 int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,

@@ -35,17 +35,15 @@
 //     The reference issues Ct + 8 global atomics per (pixel, Gaussian); this kernel issues Ct + 8 per
 //     (32-pixel block, Gaussian), all into one contiguous 144-B record.
 //   * warp-ballot skip of entries no lane blends.
-#include <cstdlib>
-
+//
+// Tried and dropped in round 2 (commit 35841d2, profiles/r6c_bwd_transposed_ab.jsonl): the TRANSPOSED formulation — lane =
+// list entry with its record in registers, the 32 pixels walked in a loop, channel and geometry gradients accumulated in
+// registers (no exchange, 16 instead of 53 shared-memory wavefronts per visit), the per-pixel recurrences turned into two
+// warp scans.  Bit-for-bit the same parity tier (34 / 34 tests), the same ~165 instructions per 32 (pixel, entry) pairs, but
+// 2.81 vs 2.01 ms at C3 and 0.63 vs 0.39 ms at C4: eleven dependent shuffles per pixel iteration at 16 warps / SM (128
+// registers) leave the schedulers idle — this kernel is bound by issue slots AND latency, not by shared memory alone.
 #include "kernels.cuh"
 #include "tile_stage.cuh"
-
-#ifndef LSX_BWD_DEFAULT_VARIANT
-#define LSX_BWD_DEFAULT_VARIANT 0
-#endif
-#ifndef LSX_BWD_T_MIN_BLOCKS
-#define LSX_BWD_T_MIN_BLOCKS 0
-#endif
 
 namespace lsx {
 
@@ -296,219 +294,14 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Transposed formulation (LSX_BWD_VARIANT=1): lane = list ENTRY, the block's 32 pixels are walked in a loop.
-//
-// A round is 32 consecutive elements of the block's compacted list, back to front (lane 0 = deepest).  Every lane keeps
-// ITS entry's record (head + Ct channels) in registers for the whole round — fetched once, straight from global/L2,
-// no shared-memory staging — and accumulates that entry's channel gradients and its 8 geometry terms over the
-// pixels IN REGISTERS: no cross-lane reduction, no weight exchange, no per-visit barrier.  The upstream gradients of
-// the 32 pixels sit in shared memory (3.5 KB at 28 channels) and are read as warp-broadcast LDS.128: the same Ct/4
-// loads feed the dot product s = <feat, dL/dpix> AND the channel-gradient FMAs (the pixel-per-lane kernel above pays
-// Ct/4 + 8 loads and an exchange of 9 values through shared memory per visit: ~53 shared-memory wavefronts per visit
-// against ~16 per pixel iteration here).
-// What was a per-pixel serial recurrence becomes two warp scans per pixel iteration:
-//     T_before(e) = T_p * prod_{i <= lane, blended} 1 / (1 - alpha_i)                 (inclusive prefix product)
-//     dL/dalpha_e = s_e T_before(e) - (B_p + sum_{i < lane} w_i s_i) / (1 - alpha_e)  (exclusive prefix sum)
-// with the per-pixel carries (T_p, B_p = sum over deeper entries of w s, started at T_final <bg, dL/dcolor>) living
-// in the registers of lane p.  The closed form equals the reference's "colour behind" recurrence (backward.cu:581-641):
-// accumulated colour behind e = (sum_{d deeper} w_d c_d) / (T_before(e) (1 - alpha_e)).
-// Pixels whose last contributor lies in front of the whole round are skipped (uniform branch), which the pixel-per-lane
-// form cannot do.  At the end of a round the 32 lanes' results go through a padded shared-memory tile so that the global
-// reductions stay coalesced: lane c issues RED.ADD.F32 for float c of one entry's contiguous gradient record at a time.
-template <int CT4, int MB>
-__global__ void __launch_bounds__(32, MB) render_bwd_t_kernel(const RenderParams p) {
-    constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
-    constexpr int GS = CT4 + 8;          // floats per packed gradient record
-    constexpr int FROW = GS | 1;         // odd row stride of the flush tile: conflict-free writes (lane = row) and reads (lane = column)
-    __shared__ __align__(16) float s_g[32 * CT4];   // upstream gradient of every blended channel at the block's 32 pixels
-    __shared__ float s_f[32 * FROW];                 // flush tile: [entry][channel gradients | geometry terms]
-    __shared__ int s_id[32];
-
-    const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
-    const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
-    const unsigned lane = threadIdx.x;
-    const int bx = tile_x * TILE_X + (warp & 1) * 8, by = tile_y * TILE_Y + (warp >> 1) * 4;
-    const int px = bx + (int)(lane & 7), py = by + (int)(lane >> 3);
-    const bool inside = px < p.W && py < p.H;
-    const size_t HW = (size_t)p.H * p.W;
-    const size_t pix = (size_t)py * p.W + px;
-
-    const uint2 range = p.ranges[tile];
-    const int n = (int)(range.y - range.x);
-
-    // ---- state of pixel `lane` ----------------------------------------------------------------------
-    float T = inside ? p.final_T[pix] : 0.f;
-    const int last_k = inside ? (int)p.k_contrib[pix] : 0;
-    const int cnt = (n > 0) ? (int)p.blk_cnt[8 * tile + warp] : 0;
-    const int n_eff = min(__reduce_max_sync(kFull, last_k), cnt);
-    if (n_eff == 0) return;
-    float Bs;  // sum over deeper blended entries of w * s, plus the background term T_final * <bg, dL/dcolor>
-    {
-        float g[CT4];
-        float bg_dot = 0.f;
-        load_pixel_gradients<CT4>(p, inside, pix, HW, (float)px, (float)py, g, bg_dot);
-        Bs = T * bg_dot;
-#pragma unroll
-        for (int q = 0; q < CT4 / 4; ++q)
-            *reinterpret_cast<float4*>(&s_g[lane * CT4 + 4 * q]) = make_float4(g[4 * q], g[4 * q + 1], g[4 * q + 2], g[4 * q + 3]);
-    }
-    __syncwarp();
-    const uint32_t g_addr = smem_u32(s_g), f_addr = smem_u32(s_f), id_addr = smem_u32(s_id);
-
-    const uint32_t* list = p.blk_list + (size_t)warp * p.list_stride + range.x;
-    const uint32_t* plist = p.point_list + range.x;
-    const int nrounds = (n_eff + 31) >> 5;
-    int k = n_eff - 1 - (int)lane;  // this lane's list element in the current round (back to front)
-    uint32_t id = (k >= 0) ? __ldg(plist + __ldg(list + k)) : 0u;
-
-    for (int r = 0; r < nrounds; ++r) {
-        const bool valid = k >= 0;
-        const int kfirst = max(n_eff - 32 - 32 * r, 0);  // smallest list element of this round
-        // ---- this lane's entry: record -> registers; next round's id in flight ----
-        float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float2 h1 = make_float2(0.f, 0.f);
-        float f[CT4];
-#pragma unroll
-        for (int c = 0; c < CT4; ++c) f[c] = 0.f;
-        if (valid) {
-            const float* rec = p.records + (size_t)id * RS;
-            h0 = __ldg(reinterpret_cast<const float4*>(rec));
-            h1 = __ldg(reinterpret_cast<const float2*>(rec + 4));
-#pragma unroll
-            for (int q = 0; q < CT4 / 4; ++q) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(rec + REC_HEAD + 4 * q));
-                f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
-            }
-        }
-        const int kn = k - 32;
-        const uint32_t id_next = (kn >= 0) ? __ldg(plist + __ldg(list + kn)) : 0u;
-
-        float df[CT4], ge[8];
-#pragma unroll
-        for (int c = 0; c < CT4; ++c) df[c] = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) ge[c] = 0.f;
-
-#pragma unroll 1
-        for (int q_ = 0; q_ < 32; ++q_) {
-            const int lk = __shfl_sync(kFull, last_k, q_);
-            if (lk <= kfirst) continue;  // every entry of this round lies behind this pixel's last contributor
-            const float pxf = (float)(bx + (q_ & 7)), pyf = (float)(by + (q_ >> 3));
-            const float dx = __fadd_rn(h0.x, -pxf), dy = __fadd_rn(h0.y, -pyf);
-            const float power = splat_power(h0.z, h0.w, h1.x, dx, dy);
-            const float G = expf(power);
-            const float alpha = splat_alpha(h1.y, G);
-            const bool blend = valid && (k < lk) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
-            if (__ballot_sync(kFull, blend) == 0) continue;
-            const float om = blend ? __fadd_rn(1.f, -alpha) : 1.f;
-            float rc;
-            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(om));
-            // inclusive prefix product of 1 / (1 - alpha) over the lanes (= entries, deepest first)
-            float pr = rc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const float t = __shfl_up_sync(kFull, pr, d);
-                pr = (lane >= (unsigned)d) ? pr * t : pr;
-            }
-            const float Tp = __shfl_sync(kFull, T, q_);
-            const float Tn = Tp * pr;  // transmittance in front of this entry
-            const float w = blend ? alpha * Tn : 0.f;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            const uint32_t ga = g_addr + (uint32_t)(q_ * CT4 * 4);
-#pragma unroll
-            for (int q = 0; q < CT4 / 4; ++q) {
-                const float4 gq = lds128(ga + q * 16);
-                s0 += f[4 * q + 0] * gq.x;
-                s1 += f[4 * q + 1] * gq.y;
-                s2 += f[4 * q + 2] * gq.z;
-                s3 += f[4 * q + 3] * gq.w;
-                df[4 * q + 0] += w * gq.x;
-                df[4 * q + 1] += w * gq.y;
-                df[4 * q + 2] += w * gq.z;
-                df[4 * q + 3] += w * gq.w;
-            }
-            const float s = (s0 + s1) + (s2 + s3);
-            // prefix sum of w * s over the lanes: inclusive in ps, exclusive (deeper entries of this round) in ex
-            float ps = w * s;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const float t = __shfl_up_sync(kFull, ps, d);
-                ps = (lane >= (unsigned)d) ? ps + t : ps;
-            }
-            float ex = __shfl_up_sync(kFull, ps, 1);
-            ex = (lane == 0u) ? 0.f : ex;
-            const float Bp = __shfl_sync(kFull, Bs, q_);
-            const float dL_dalpha = s * Tn - (Bp + ex) * rc;
-            const float u = blend ? G * dL_dalpha : 0.f;  // G * dL/dalpha
-            const float ku = h1.y * u;                   // opacity * G * dL/dalpha = G * dL/dG
-            const float kdx = ku * dx, kdy = ku * dy;
-            const float mx = -kdx * h0.z - kdy * h0.w;
-            const float my = -kdy * h1.x - kdx * h0.w;
-            ge[0] += mx;
-            ge[1] += my;
-            ge[2] += fabsf(mx);
-            ge[3] += fabsf(my);
-            ge[4] += kdx * dx;
-            ge[5] += kdx * dy;
-            ge[6] += kdy * dy;
-            ge[7] += u;
-            // carries of pixel q_ past this round
-            const float prl = __shfl_sync(kFull, pr, 31), psl = __shfl_sync(kFull, ps, 31);
-            if (lane == (unsigned)q_) {
-                T = Tp * prl;
-                Bs = Bp + psl;
-            }
-        }
-
-        // ---- flush: lane = entry  ->  tile  ->  lane = float of one entry's contiguous gradient record ----
-#pragma unroll
-        for (int c = 0; c < CT4; ++c) sts32(f_addr + (uint32_t)((lane * FROW + c) * 4), df[c]);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sts32(f_addr + (uint32_t)((lane * FROW + CT4 + c) * 4), ge[c]);
-        sts32i(id_addr + lane * 4u, (int)id);
-        __syncwarp();
-        const int m = min(32, n_eff - 32 * r);
-#pragma unroll 1
-        for (int e = 0; e < m; ++e) {
-            float* grec = p.grad_records + (size_t)lds32i(id_addr + (uint32_t)(e * 4)) * GS;
-#pragma unroll
-            for (int c0 = 0; c0 < GS; c0 += 32) {
-                const int c = c0 + (int)lane;
-                if (c < GS) {
-                    float v;
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(f_addr + (uint32_t)((e * FROW + c) * 4)) : "memory");
-                    if (v != 0.f) atomicAdd(grec + c, v);
-                }
-            }
-        }
-        __syncwarp();
-        id = id_next;
-        k = kn;
-    }
-}
-
 // At 28 channels 20 CTAs / SM are requested: ptxas otherwise settles on more registers than the 96 that fit.
-// LSX_BWD_VARIANT: 0 = pixel-per-lane kernel, 1 = entry-per-lane (transposed) kernel.  Read once.
-int bwd_variant() {
-    static const int v = [] {
-        const char* e = getenv("LSX_BWD_VARIANT");
-        return e ? atoi(e) : LSX_BWD_DEFAULT_VARIANT;
-    }();
-    return v;
-}
-
 template <int CT4>
 int launch_bwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    constexpr int MB = (CT4 == 28) ? 20 : 0;
+    const size_t smem = ListStage<RS>::kSmemBytes;
     const long long blocks = (long long)p.grid_x * p.grid_y * 8;
-    if (bwd_variant() == 1) {
-        render_bwd_t_kernel<CT4, LSX_BWD_T_MIN_BLOCKS><<<(unsigned)blocks, 32, 0, stream>>>(p);
-    } else {
-        constexpr int MB = (CT4 == 28) ? 20 : 0;
-        const size_t smem = ListStage<RS>::kSmemBytes;
-        render_bwd_kernel<CT4, MB><<<(unsigned)blocks, 32, smem, stream>>>(p);
-    }
+    render_bwd_kernel<CT4, MB><<<(unsigned)blocks, 32, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

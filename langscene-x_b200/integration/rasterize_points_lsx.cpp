@@ -155,6 +155,7 @@ RasterizeGaussiansBackwardCUDA(const torch::Tensor& background, const torch::Ten
         a.dL_dall_map = dL_dall_map.data_ptr<float>();
         a.stream = current_stream();
         a.accumulate_param_grads = 0;
+        a.binning_bytes = (uint64_t)binningBuffer.numel();   // the list capacity is recovered from the buffer's size
         if (lsx_rasterize_backward(&a) != 0) AT_ERROR(lsx_last_error());
     }
     return std::make_tuple(dL_dmeans2D, dL_dmeans2D_abs, dL_dcolors, dL_dlanguage_feature, dL_dlanguage_feature_instance,

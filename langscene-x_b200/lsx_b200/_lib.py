@@ -32,6 +32,7 @@ class ForwardArgs(ctypes.Structure):
         ("binning_alloc", ALLOC_FN), ("binning_user", c_void_p),
         ("image_alloc", ALLOC_FN), ("image_user", c_void_p),
         ("stream", c_void_p),
+        ("binning_capacity_hint", c_int32),
     ]
 
 
@@ -55,6 +56,7 @@ class BackwardArgs(ctypes.Structure):
         ("dL_drotations", c_void_p), ("dL_dall_map", c_void_p),
         ("stream", c_void_p),
         ("accumulate_param_grads", c_int32),
+        ("binning_bytes", c_uint64),
     ]
 
 
@@ -139,9 +141,11 @@ EXPORTS = {
     "lsx_rows_pack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_rows_unpack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),
-    "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+    "lsx_debug_sorted_keys": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p,
                                         c_void_p, c_void_p]),
-    "lsx_render_stats": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "lsx_binning_capacity": (c_int32, [c_size_t, c_int32, c_int32]),
+    "lsx_render_stats": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+                                   c_void_p]),
     "lsx_kernel_launch_count": (c_uint64, []),
     "lsx_profile_enable": (None, [c_int32]),
     "lsx_profile_read": (c_int32, [POINTER(c_float), c_int32]),

@@ -66,7 +66,10 @@ class LoopConfig:
     reg3d_samples: int = 800
     optimise_pose: bool = True           # optim_pose (:67)
     densify_stats: bool = True
-    overlap_allreduce: bool = True
+    # per-group asynchronous all-reduces issued while the last view's backward is still running, instead of ONE blocking
+    # collective after it.  Measured at C4 on 2 GPUs (profiles/r6e_c4loop_n2*.json): 11.47 vs 11.08 ms per step — five small
+    # collectives and NCCL's CTAs competing with the wrapper's backward cost more than the 0.28 ms they hide; off by default.
+    overlap_allreduce: bool = False
 
 
 @dataclass

@@ -82,6 +82,30 @@ def _check(status, what, *allocs):
     _lib.check(status, what)
 
 
+# ---- speculative binning capacity (lsx_forward_args.binning_capacity_hint) ----------------------------------------------
+# The list length of a forward call is close to that of the previous calls on the same scene (same Gaussian count, same image
+# size): 1.25 x the largest of the last few is handed to the library as the capacity, so that it need not drain the stream to
+# learn the exact length.  A wrong guess costs one repeated binning pass inside the library, never a wrong result.
+# LSX_SPECULATIVE_BINNING=0 switches it off (the reference's behaviour: one blocking read in the middle of every forward).
+import os as _os
+
+_SPECULATE = _os.environ.get("LSX_SPECULATIVE_BINNING", "1") != "0"
+_recent_rendered = {}
+
+
+def _capacity_hint(key):
+    hist = _recent_rendered.get(key)
+    if not _SPECULATE or not hist:
+        return 0
+    return min(int(1.25 * max(hist)) + 4096, 0x7fffff00)
+
+
+def _remember_rendered(key, rendered):
+    hist = _recent_rendered.setdefault(key, [])
+    hist.append(int(rendered))
+    del hist[:-4]
+
+
 def _stream_handle(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -159,8 +183,12 @@ def rasterize_gaussians(
         a.out_all_map, a.out_plane_depth = out_all_map.data_ptr(), out_plane_depth.data_ptr()
         a.geom_alloc, a.binning_alloc, a.image_alloc = geom.fn, binning.fn, image.fn
         a.stream = _stream_handle(device)
+        hint_key = (device.index, P, H, W, n_blend)
+        a.binning_capacity_hint = 0 if debug else _capacity_hint(hint_key)
         rendered = ctypes.c_int32(0)
         _check(lib.lsx_rasterize_forward(ctypes.byref(a), ctypes.byref(rendered)), "rasterize_gaussians", geom, binning, image)
+
+        _remember_rendered(hint_key, rendered.value)
 
     return (int(rendered.value), out_color, out_lang, out_inst, radii, out_observe, out_all_map, out_plane_depth,
             geom.tensor, binning.tensor, image.tensor)
@@ -281,6 +309,7 @@ def rasterize_gaussians_backward(
             a.dL_dscales, a.dL_drotations, a.dL_dall_map = g_scales.data_ptr(), g_rot.data_ptr(), g_all_map.data_ptr()
             a.stream = _stream_handle(device)
             a.accumulate_param_grads = acc_mask
+            a.binning_bytes = int(binningBuffer.numel()) if binningBuffer is not None else 0
             _lib.check(lib.lsx_rasterize_backward(ctypes.byref(a)), "rasterize_gaussians_backward")
 
     return (g_means2D, g_means2D_abs, g_colors, g_lang, g_inst, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot,
@@ -332,7 +361,7 @@ def render_stats(num_rendered, geomBuffer, binningBuffer, imageBuffer, P, image_
     with torch.cuda.device(device):
         out = torch.empty(8, dtype=torch.int64, device=device)
         _lib.check(lib.lsx_render_stats(int(P), int(image_width), int(image_height), int(num_rendered), int(n_blend_channels),
-                                        _ptr(geomBuffer), _ptr(binningBuffer), _ptr(imageBuffer), out.data_ptr(),
-                                        _stream_handle(device)), "render_stats")
+                                        _ptr(geomBuffer), _ptr(binningBuffer), int(binningBuffer.numel()), _ptr(imageBuffer),
+                                        out.data_ptr(), _stream_handle(device)), "render_stats")
         v = out.cpu().tolist()
     return {"S": v[0], "B": v[1], "V": v[2], "Vb": v[3], "L": v[4], "R": int(num_rendered)}

@@ -83,7 +83,10 @@ def parse_new_buffers(geom, binning, img, P, R, W, H, n_blend):
     from lsx_b200 import _lib
     lib = _lib.load()
     lay = _lib.ScratchLayout()
-    _lib.check(lib.lsx_scratch_layout_query(P, W, H, R, n_blend, ctypes.byref(lay)), "layout")
+    # the binning scratch is carved for a list CAPACITY >= R (R rounded up to 64, or the speculative hint of the call)
+    cap = int(lib.lsx_binning_capacity(int(binning.numel()), W, H)) if R > 0 else 0
+    assert cap >= R, (cap, R)
+    _lib.check(lib.lsx_scratch_layout_query(P, W, H, cap, n_blend, ctypes.byref(lay)), "layout")
     N = W * H
     T = ((W + 15) // 16) * ((H + 15) // 16)
     out = {}
@@ -101,12 +104,12 @@ def parse_new_buffers(geom, binning, img, P, R, W, H, n_blend):
     if R > 0:
         out["point_list"] = _view(binning, lay.point_list, R, torch.int32)
         out["masks"] = _view(binning, lay.masks, R, torch.uint8)
-        out["blk_list"] = _view(binning, lay.blk_list, 8 * R, torch.int32).view(8, R)
+        out["blk_list"] = _view(binning, lay.blk_list, 8 * cap, torch.int32).view(8, cap)
         out["blk_cnt"] = _view(binning, lay.blk_cnt, 8 * T, torch.int32).view(T, 8)
         out["k_contrib"] = _view(img, lay.k_contrib, N, torch.int32)
         keys = torch.empty(R, dtype=torch.int64, device=geom.device)
-        _lib.check(lib.lsx_debug_sorted_keys(P, W, H, R, n_blend, geom.data_ptr(), binning.data_ptr(), img.data_ptr(),
-                                             keys.data_ptr(), torch.cuda.current_stream().cuda_stream), "debug keys")
+        _lib.check(lib.lsx_debug_sorted_keys(P, W, H, R, n_blend, geom.data_ptr(), binning.data_ptr(), int(binning.numel()),
+                                             img.data_ptr(), keys.data_ptr(), torch.cuda.current_stream().cuda_stream), "debug keys")
         out["keys"] = keys
     return out
 

@@ -203,3 +203,16 @@ def test_module_autograd_plumbing_with_a_stub_native_layer(monkeypatch):
             assert (v.grad is None) == (k in sunk), k
         assert m2.grad is not None                      # screen-space gradients always reach autograd (densification)
         assert (seen["sink"][0] is sink) and seen["sink"][1] == bool(sink)
+
+
+def test_binning_capacity_is_recovered_from_the_buffer_size():
+    """The backward pass and the debug helpers get only the binning buffer: its list capacity (a multiple of 64) must be
+    recoverable from its size, for every capacity and image size (pure host arithmetic)."""
+    from lsx_b200 import _lib
+    lib = _lib.load()
+    lay = _lib.ScratchLayout()
+    for W, H in ((64, 64), (720, 480), (1920, 1080)):
+        for cap in (0, 64, 128, 4096, 1_000_000 // 64 * 64, 26_500_032):
+            assert lib.lsx_scratch_layout_query(10, W, H, cap, 27, ctypes.byref(lay)) == 0
+            assert lib.lsx_binning_capacity(lay.binning_bytes, W, H) == cap, (W, H, cap)
+            assert lib.lsx_binning_capacity(lay.binning_bytes + 8, W, H) == -1        # not a size any capacity produces

@@ -535,3 +535,40 @@ def test_knn_matches_reference_and_golden():
         if P <= 5000:
             from oracle import oracle as orc
             assert np.array_equal(got.cpu().numpy().view(np.uint32), orc.knn_mean_dist2(pts.cpu().numpy()).view(np.uint32))
+
+
+def test_speculative_binning_capacity_gives_the_exact_result():
+    """lsx_forward_args.binning_capacity_hint: the kernels behind the duplicate-offset scan are enqueued for a guessed list
+    capacity before the host knows num_rendered (no stream drain in the middle of the forward pass).  A generous hint, a
+    hint that is too small (binning + render repeated inside the call) and the exact path must give identical results:
+    num_rendered, every image bit for bit, sorted keys / point list / tile ranges / n_contrib, and gradients to tolerance."""
+    from lsx_b200 import ops
+    P, W, H, F = 30_000, 320, 208, 16
+    scene, cam, grads = _scene(P, W, H, F, seed=77)
+    fargs = hz.native_forward_args(scene, cam, torch.tensor([0.1, 0.0, 0.2], device="cuda:0"), F)
+    key = (0, P, H, W, 3 + F + 3 + 5)
+    results = {}
+    for mode in ("exact", "generous", "too_small", "exact_fit"):
+        ops._recent_rendered.pop(key, None)
+        if mode != "exact":
+            R0 = results["exact"][0]["num_rendered"]
+            ops._recent_rendered[key] = [{"generous": R0, "too_small": R0 // 3, "exact_fit": int((R0 - 4096) / 1.25)}[mode]]
+        fwd, bwd = hz.run_native(ops, fargs, grads)
+        torch.cuda.synchronize()
+        buf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, fwd["num_rendered"], W, H, 3 + F + 3 + 5)
+        results[mode] = (fwd, bwd, buf)
+    ops._recent_rendered.pop(key, None)
+    f0, b0, u0 = results["exact"]
+    assert f0["num_rendered"] > 0
+    caps = {m: results[m][2]["blk_list"].shape[1] for m in results}
+    assert caps["generous"] > caps["exact"] and caps["too_small"] == caps["exact"], caps     # too small -> redone with the exact size
+    for mode in ("generous", "too_small", "exact_fit"):
+        f, b, u = results[mode]
+        assert f["num_rendered"] == f0["num_rendered"], mode
+        for k in ("color", "language_feature", "instance_feature", "all_map", "plane_depth", "radii", "out_observe"):
+            assert torch.equal(f[k], f0[k]), (mode, k)
+        for k in ("keys", "point_list", "ranges", "n_contrib", "k_contrib", "masks", "blk_cnt"):
+            assert torch.equal(u[k], u0[k]), (mode, k)
+        assert _bit_equal(u["final_T"], u0["final_T"]), mode
+        for k in hz.BWD_NAMES:
+            assert hz.rel_err(b[k], b0[k]) < BWD_TOL, (mode, k)
