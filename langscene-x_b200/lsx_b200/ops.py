@@ -82,14 +82,17 @@ def _check(status, what, *allocs):
     _lib.check(status, what)
 
 
-# ---- speculative binning capacity (lsx_forward_args.binning_capacity_hint) ----------------------------------------------
+# ---- speculative binning capacity (lsx_forward_args.binning_capacity_hint), OFF by default -------------------------------
 # The list length of a forward call is close to that of the previous calls on the same scene (same Gaussian count, same image
-# size): 1.25 x the largest of the last few is handed to the library as the capacity, so that it need not drain the stream to
-# learn the exact length.  A wrong guess costs one repeated binning pass inside the library, never a wrong result.
-# LSX_SPECULATIVE_BINNING=0 switches it off (the reference's behaviour: one blocking read in the middle of every forward).
+# size): with LSX_SPECULATIVE_BINNING=1, 1.25 x the largest of the last few is handed to the library as the capacity, so that
+# it need not drain the stream in the middle of the forward pass to learn the exact length.  A wrong guess costs one repeated
+# binning pass inside the library, never a wrong result (tests/test_parity_gpu.py).  Measured (profiles/r6f_sweep_*.jsonl):
+# no gain in a training-shaped loop — the host is blocked in that read while the GPU is still busy with the previous
+# backward pass, so the bubble is one kernel-launch latency, and the 25 % of padded list slots cost as much in the tile sort:
+# C3 3.761 vs 3.758 ms, C4 0.954 vs 0.960, C1 0.360 vs 0.321.  Kept for callers whose stream is otherwise empty at that point.
 import os as _os
 
-_SPECULATE = _os.environ.get("LSX_SPECULATIVE_BINNING", "1") != "0"
+_SPECULATE = _os.environ.get("LSX_SPECULATIVE_BINNING", "0") == "1"
 _recent_rendered = {}
 
 

@@ -543,6 +543,7 @@ def test_speculative_binning_capacity_gives_the_exact_result():
     hint that is too small (binning + render repeated inside the call) and the exact path must give identical results:
     num_rendered, every image bit for bit, sorted keys / point list / tile ranges / n_contrib, and gradients to tolerance."""
     from lsx_b200 import ops
+    ops._SPECULATE = True               # off by default (LSX_SPECULATIVE_BINNING=1 enables it)
     P, W, H, F = 30_000, 320, 208, 16
     scene, cam, grads = _scene(P, W, H, F, seed=77)
     fargs = hz.native_forward_args(scene, cam, torch.tensor([0.1, 0.0, 0.2], device="cuda:0"), F)
@@ -558,6 +559,7 @@ def test_speculative_binning_capacity_gives_the_exact_result():
         buf = hz.parse_new_buffers(fwd["geom"], fwd["binning"], fwd["img"], P, fwd["num_rendered"], W, H, 3 + F + 3 + 5)
         results[mode] = (fwd, bwd, buf)
     ops._recent_rendered.pop(key, None)
+    ops._SPECULATE = False
     f0, b0, u0 = results["exact"]
     assert f0["num_rendered"] > 0
     caps = {m: results[m][2]["blk_list"].shape[1] for m in results}
