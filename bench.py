@@ -379,30 +379,46 @@ def algorithmic_bytes(P, P_vis, R, W, H, M, F, Fi):
 
 
 def run_cpu_sample(threads=None):
-    """The CPU restatement on a bounded sample: the C3 generator scaled by 1/4 in pixels and Gaussians
-    (960x540, 250 000 Gaussians, same splat size in pixels => same per-pixel list statistics), fwd+bwd, best of 2."""
+    """The reference's CPU-executable path on a bounded sample (BASELINE north_star): the PyTorch SH -> RGB and
+    world-covariance preprocess the reference can run instead of the CUDA one (pipe.convert_SHs_python / compute_cov3D_python,
+    gaussian_renderer/__init__.py:101-121; restated in oracle/preprocess_torch_oracle.py and pinned to the reference's own
+    functions) with all host threads, forward AND autograd backward, feeding the per-pixel compositing restatement
+    (oracle/lsx_oracle.c, OpenMP over tiles) forward + backward.  Sample: the C3 generator scaled by 1/4 in pixels and
+    Gaussians (960x540, 250 000 Gaussians, same splat size in pixels => same per-pixel list statistics); best of 2."""
     from oracle import oracle as orc
+    from oracle import preprocess_torch_oracle as pto
     from lsx_b200.synthetic import make_all_map, make_camera, make_scene, make_upstream_grads
     P, W, H, F = 250_000, 960, 540, 16
     if threads:
         orc.set_num_threads(threads)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     scene, cam = make_scene(P, W, H, F=F, seed=0), make_camera(W, H)
     am, g = make_all_map(scene, cam), make_upstream_grads(W, H, F)
-    n = lambda t: t.numpy()
-    best = 1e30
+    n = lambda t: t.detach().numpy()
+    best, parts = 1e30, None
     for _ in range(2):
         t0 = time.perf_counter()
+        shs, scales, rots = (t.clone().requires_grad_(True) for t in (scene.shs, scene.scales, scene.rotations))
+        rgb = pto.sh_to_rgb(3, shs, scene.means3D, cam.campos)
+        cov = pto.world_covariance(scales, 1.0, rots)
+        t1 = time.perf_counter()
         o = orc.rasterize_forward(n(scene.means3D), n(scene.opacities), n(cam.viewmatrix), n(cam.projmatrix), n(cam.campos),
-                                  W, H, cam.tanfovx, cam.tanfovy, [0, 0, 0], shs=n(scene.shs), scales=n(scene.scales),
-                                  rotations=n(scene.rotations), language_feature=n(scene.language_feature),
-                                  instance_feature=n(scene.instance_feature), all_map=n(am))
-        orc.rasterize_backward(o, n(g["color"]), n(g["language_feature"]), n(g["instance_feature"]), n(g["all_map"]),
-                               n(g["plane_depth"]))
-        best = min(best, time.perf_counter() - t0)
-    return {"value": W * H / best / 1e6, "unit": "MPix/s", "cores": orc.num_threads(), "kind": "port",
-            "sample": f"oracle/lsx_oracle.c (OpenMP) fwd+bwd, best of 2, on the C3 generator scaled 1/4: {P} Gaussians, "
-                      f"{W}x{H}, F=16 (+3 instance, +5 map), R={o['num_rendered']}, {best:.2f} s/iter; "
-                      f"host has {os.cpu_count()} logical cores"}
+                                  W, H, cam.tanfovx, cam.tanfovy, [0, 0, 0], colors_precomp=n(rgb), cov3D_precomp=n(cov),
+                                  language_feature=n(scene.language_feature), instance_feature=n(scene.instance_feature),
+                                  all_map=n(am))
+        gb = orc.rasterize_backward(o, n(g["color"]), n(g["language_feature"]), n(g["instance_feature"]), n(g["all_map"]),
+                                    n(g["plane_depth"]))
+        t2 = time.perf_counter()
+        torch.autograd.backward([rgb, cov], [torch.from_numpy(gb["colors"]), torch.from_numpy(gb["cov3D"])])
+        t3 = time.perf_counter()
+        if t3 - t0 < best:
+            best, parts = t3 - t0, (t1 - t0, t2 - t1, t3 - t2)
+    return {"value": W * H / best / 1e6, "unit": "MPix/s", "cores": max(orc.num_threads(), torch.get_num_threads()), "kind": "port",
+            "sample": f"fwd+bwd, best of 2, on the C3 generator scaled 1/4 ({P} Gaussians, {W}x{H}, F=16 + 3 instance + 5 map "
+                      f"channels, R={o['num_rendered']}): torch-CPU eval_sh + covariance (the reference's Python preprocess path, "
+                      f"{torch.get_num_threads()} threads) {parts[0]:.2f} s, compositing restatement oracle/lsx_oracle.c fwd+bwd "
+                      f"({orc.num_threads()} OpenMP threads) {parts[1]:.2f} s, torch autograd through the preprocess {parts[2]:.2f} s; "
+                      f"{best:.2f} s/iter; host has {os.cpu_count()} logical cores; not bit-comparable with the CUDA path"}
 
 
 def main():
