@@ -122,7 +122,7 @@ class ClockSampler:
 
 
 def build_views(cfg_name, device, rank=0, world=1, views=1, seed=0):
-    """The shared scene plus this rank's cameras: global view v = rank*views + i of world*views views on the arc
+    """The shared scene plus this rank's cameras: global view v = rank + world*i of world*views views on the arc
     yaw = -15..+15 degrees; a single view overall is the yaw-0 camera."""
     from lsx_b200.synthetic import CONFIGS, make_all_map, make_camera, make_scene, make_upstream_grads
     import harness as hz
@@ -133,7 +133,7 @@ def build_views(cfg_name, device, rank=0, world=1, views=1, seed=0):
     total = world * views
     out = []
     for i in range(views):
-        v = rank * views + i
+        v = rank + world * i      # round-robin over the arc: every rank gets the same spread of view costs
         yaw = 0.0 if total == 1 else (-15.0 + 30.0 * v / (total - 1))
         cam = make_camera(c["W"], c["H"], yaw_deg=yaw).to(device)
         am = make_all_map(scene, cam)
@@ -263,35 +263,43 @@ def _pin_views(views, grads):
 
 class HostFeeder:
     """Per-view host inputs (camera matrices + colour-supervision gradient) in pinned memory, copied to the device on
-    a side stream into two alternating buffers, so that the copy of view i+1 overlaps the compute of view i.  The
-    first view of every step is copied inside the step without overlap; all copies are inside the timed region."""
+    a side stream into two alternating buffers: while view i is computed, the copy of the NEXT view — cyclically, i.e. the
+    first view of the next step while the last view of this one runs — is in flight.  Every copy is issued inside the timed
+    region; only the very first one (before the first step) is not overlapped."""
 
     def __init__(self, views, grads):
         dev = grads["color"].device
         self.cams, self.gcol, self.h2d_bytes = _pin_views(views, grads)
+        self.n = len(views)
         self.stream = torch.cuda.Stream(device=dev)
         self.buf = [(torch.empty_like(self.cams[0], device=dev), torch.empty_like(grads["color"])) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         for e in self.free:
             e.record()
+        self.issued = 0        # copies issued so far; copy k goes to buffer k & 1 and carries view k % n
+        self.consumed = 0
 
-    def fetch(self, i):
-        """enqueue the copy of view i into buffer i & 1 (after the compute that last used it)"""
-        slot = i & 1
+    def _issue(self):
+        slot, i = self.issued & 1, self.issued % self.n
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.free[slot])
             self.buf[slot][0].copy_(self.cams[i], non_blocking=True)
             self.buf[slot][1].copy_(self.gcol, non_blocking=True)
             self.ready[slot].record(self.stream)
+        self.issued += 1
 
-    def get(self, i):
-        slot = i & 1
+    def get(self):
+        """the next view's inputs (views come in cyclic order); keeps one further copy in flight"""
+        while self.issued < self.consumed + 2:
+            self._issue()
+        slot = self.consumed & 1
         torch.cuda.current_stream().wait_event(self.ready[slot])
         return self.buf[slot]
 
-    def release(self, i):
-        self.free[i & 1].record()
+    def release(self):
+        self.free[self.consumed & 1].record()
+        self.consumed += 1
 
 
 def e2e_stepper(mod, views, grads, arena, world):
@@ -306,17 +314,14 @@ def e2e_stepper(mod, views, grads, arena, world):
     def step():
         arena.zero_()
         acc = None
-        feeder.fetch(0)
         for i, vw in enumerate(views):
-            if i + 1 < len(views):
-                feeder.fetch(i + 1)
-            d_cam, d_gcol = feeder.get(i)
+            d_cam, d_gcol = feeder.get()
             fargs = list(vw["fargs"])
             fargs[11], fargs[12], fargs[19] = d_cam[:16].view(4, 4), d_cam[16:32].view(4, 4), d_cam[32:35]
             g["color"] = d_gcol
             fwd = dict(zip(hz.FWD_NAMES, mod.rasterize_gaussians(*fargs)))
             bwd = dict(zip(hz.BWD_NAMES, mod.rasterize_gaussians_backward(*hz.native_backward_args(fargs, fwd, g))))
-            feeder.release(i)
+            feeder.release()
             arena.accumulate({gname: bwd[k] for k, gname in BWD_TO_GROUP.items()})
             acc = fwd["color"].sum() if acc is None else acc + fwd["color"].sum()
         if world > 1:
@@ -345,11 +350,8 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
         for p in ams + [m2, m2a]:
             p.grad = None
         acc = None
-        feeder.fetch(0)
         for i, am in enumerate(ams):
-            if i + 1 < len(ams):
-                feeder.fetch(i + 1)
-            d_cam, d_gcol = feeder.get(i)
+            d_cam, d_gcol = feeder.get()
             s = GaussianRasterizationSettings(c0.H, c0.W, c0.tanfovx, c0.tanfovy, bg, 1.0, d_cam[:16].view(4, 4),
                                               d_cam[16:32].view(4, 4), 3, d_cam[32:35], False, True, False, True)
             out = GaussianRasterizer(s, grad_buffers=sink, accumulate=i > 0)(
@@ -360,7 +362,7 @@ def module_e2e_stepper(scene, views, grads, bg, F, arena, world):
             torch.autograd.backward([color, lf, li, amap, depth],
                                     [d_gcol, grads["language_feature"], grads["instance_feature"], grads["all_map"],
                                      grads["plane_depth"]])
-            feeder.release(i)
+            feeder.release()
             acc = color.sum() if acc is None else acc + color.sum()
         if world > 1:
             arena.all_reduce()

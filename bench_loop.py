@@ -265,39 +265,45 @@ def allreduce_parity(loop, view_of, rank, world, v_per_gpu, n_views, P, cfg, ste
 
 # ---- end-to-end feeder: per-view supervision from pinned host memory ---------------------------------------------------------
 class TargetFeeder:
-    """gt image, language map, mask, weight map and the camera of every local view live in pinned host memory and are copied
-    to the device on a side stream into two alternating slots, inside the timed region (the copy of view i + 1 overlaps
-    the compute of view i; the first view of a step is not overlapped)."""
+    """Ground-truth image, language map (fp16 on the wire, widened on the device), mask, weight map and the camera of every
+    local view live in pinned host memory and are copied to the device on a side stream into two alternating slots, inside
+    the timed region: while view i is computed the copy of the next view — cyclically, the first view of the next step under
+    the last view of this one — is in flight."""
 
     def __init__(self, views):
         dev = views[0].gt_image.device
-        self.views = views
-        pack = lambda vw: torch.cat([vw.gt_image.flatten(), vw.gt_language.flatten(), vw.language_mask.flatten(),
-                                     vw.image_weight.flatten(), vw.viewmatrix.flatten(), vw.projmatrix.flatten(),
-                                     vw.campos.flatten()])
-        self.host = [pack(vw).cpu().pin_memory() for vw in views]
-        self.n = self.host[0].numel()
-        self.bytes_per_step = sum(h.numel() * 4 for h in self.host)
+        self.views, self.n = views, len(views)
+        f32 = lambda vw: torch.cat([vw.gt_image.flatten(), vw.language_mask.flatten(), vw.image_weight.flatten(),
+                                    vw.viewmatrix.flatten(), vw.projmatrix.flatten(), vw.campos.flatten()])
+        self.host32 = [f32(vw).cpu().pin_memory() for vw in views]
+        self.host16 = [vw.gt_language.flatten().half().cpu().pin_memory() for vw in views]
+        self.bytes_per_step = sum(h.numel() * 4 for h in self.host32) + sum(h.numel() * 2 for h in self.host16)
         self.stream = torch.cuda.Stream(device=dev)
-        self.slot = [torch.empty(self.n, device=dev) for _ in range(2)]
+        self.slot32 = [torch.empty(self.host32[0].numel(), device=dev) for _ in range(2)]
+        self.slot16 = [torch.empty(self.host16[0].numel(), device=dev, dtype=torch.float16) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
         for e in self.free:
             e.record()
+        self.issued = self.consumed = 0
 
-    def fetch(self, i):
-        s = i & 1
+    def _issue(self):
+        s, i = self.issued & 1, self.issued % self.n
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(self.free[s])
-            self.slot[s].copy_(self.host[i], non_blocking=True)
+            self.slot32[s].copy_(self.host32[i], non_blocking=True)
+            self.slot16[s].copy_(self.host16[i], non_blocking=True)
             self.ready[s].record(self.stream)
+        self.issued += 1
 
-    def view(self, i):
-        """the View of local view i with every tensor pointing into the freshly copied slot"""
+    def next_view(self):
+        """the View of the next local view (cyclic order) with every tensor pointing into the freshly copied slot"""
         from lsx_b200.field_loop import View
-        s = i & 1
+        while self.issued < self.consumed + 2:
+            self._issue()
+        s = self.consumed & 1
         torch.cuda.current_stream().wait_event(self.ready[s])
-        vw, buf = self.views[i], self.slot[s]
+        vw, buf = self.views[self.consumed % self.n], self.slot32[s]
         H, W, F = vw.H, vw.W, vw.gt_language.shape[0]
         o = 0
 
@@ -306,14 +312,16 @@ class TargetFeeder:
             t = buf[o:o + n].view(shape)
             o += n
             return t
-        gt_image, gt_lang = take(3 * H * W, (3, H, W)), take(F * H * W, (F, H, W))
+        gt_image = take(3 * H * W, (3, H, W))
         mask, weight = take(H * W, (H, W)), take(H * W, (H, W))
         vm, pm, cp = take(16, (4, 4)), take(16, (4, 4)), take(3, (3,))
+        gt_lang = self.slot16[s].view(F, H, W).float()
         return View(index=vw.index, W=W, H=H, tanfovx=vw.tanfovx, tanfovy=vw.tanfovy, viewmatrix=vm, projmatrix=pm, campos=cp,
                     gt_image=gt_image, gt_language=gt_lang, language_mask=mask, image_weight=weight)
 
-    def release(self, i):
-        self.free[i & 1].record()
+    def release(self):
+        self.free[self.consumed & 1].record()
+        self.consumed += 1
 
 
 # ---- the bench line -----------------------------------------------------------------------------------------------------------
@@ -375,24 +383,15 @@ def run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler):
     feeder = TargetFeeder(views)
 
     def e2e_step():
-        feeder.fetch(0)
         if new:
-            # FieldLoop.step wants the views up front; stage them one ahead of the compute through the two slots
-            def gen():
-                for i in range(len(views)):
-                    if i + 1 < len(views):
-                        feeder.fetch(i + 1)
-                    yield feeder.view(i)
-            out = loop_step_streamed(loop, gen(), si, feeder)
+            out = loop_step_streamed(loop, si, feeder)
         else:
             tot = None
             loop.opt.zero_grad(set_to_none=True)
             loop.cam_opt.zero_grad(set_to_none=True)
             for i in range(len(views)):
-                if i + 1 < len(views):
-                    feeder.fetch(i + 1)
-                l = loop._view(feeder.view(i), si[i] if si is not None else None)
-                feeder.release(i)
+                l = loop._view(feeder.next_view(), si[i] if si is not None else None)
+                feeder.release()
                 tot = l if tot is None else tot + l
             if world > 1:
                 for t in list(loop.p.values()) + [loop.poses]:
@@ -463,7 +462,7 @@ def run(args, emit, rank, local_rank, world, device, time_loop, ClockSampler):
     emit(out)
 
 
-def loop_step_streamed(loop, view_iter, si, feeder):
+def loop_step_streamed(loop, si, feeder):
     """FieldLoop.step with the views arriving one by one from the feeder (same work as FieldLoop.step)."""
     from lsx_b200.multiview import PendingReduce
     with torch.cuda.device(loop.device):
@@ -471,11 +470,11 @@ def loop_step_streamed(loop, view_iter, si, feeder):
         delta = loop._delta.zero_() if loop.cfg.densify_stats else None
         if loop.cfg.optimise_pose:
             loop.grads.views["pose"].zero_()
-        n = len(feeder.views)
+        n = feeder.n
         totals = {}
-        for i, vw in enumerate(view_iter):
-            res = loop._view(vw, i == 0, i == n - 1, si[i] if si is not None else None, pending, delta)
-            feeder.release(i)
+        for i in range(n):
+            res = loop._view(feeder.next_view(), i == 0, i == n - 1, si[i] if si is not None else None, pending, delta)
+            feeder.release()
             for k, v in res.items():
                 totals.setdefault(k, []).append(v)
         if loop.world > 1:

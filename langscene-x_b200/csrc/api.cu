@@ -451,7 +451,7 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
             {
                 StageTimer _t(LSX_STAGE_FOOTPRINT_MASKS, stream);
                 r2 = launch_footprint_masks(num_tiles, im.ranges, bn.point_list, gm.records, rs, grid_x, bn.masks, bn.blk_list,
-                                            (size_t)cap, bn.blk_cnt, stream, debug);
+                                            (size_t)cap, bn.blk_cnt, P, stream, debug);
             }
             if (r2) return r2;
         } else {
@@ -460,6 +460,7 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
         }
         RenderParams rp{};
         rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
+        rp.P = P; rp.R = cap;
         rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
         rp.n_channels = nch; rp.rec_stride = rs;
         rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;
@@ -583,6 +584,7 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     if (R > 0) {
         RenderParams rp{};
         rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y; rp.focal_x = focal_x; rp.focal_y = focal_y;
+        rp.P = P; rp.R = cap;
         rp.F = F; rp.Fi = Fi; rp.include_feature = a->include_feature; rp.render_geo = a->render_geo;
         rp.n_channels = nch; rp.rec_stride = rs;
         rp.ranges = im.ranges; rp.point_list = bn.point_list; rp.masks = bn.masks; rp.records = gm.records;

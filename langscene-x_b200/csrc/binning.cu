@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
         const uint32_t sy = __shfl_sync(kFull, rmin.y, (int)s);
         const uint32_t sp = __shfl_sync(kFull, pre, (int)s);
         if (j < total && base + j < cap) {
+            LSX_CHECK_INDEX(sg, P, "emitted Gaussian id");
             const uint32_t t = j - sp;
             const uint32_t row = t / sw, col = t - row * sw;  // row-major over the rectangle, y outer (duplicateWithKeys)
             tile_keys[base + j] = (sy + row) * grid_x + (sx + col);

@@ -2,6 +2,7 @@
 // Everything here is written for sm_100a only (no fallback paths).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdio>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -37,6 +38,27 @@ void count_launch(int n = 1);
             return -3;                                                                           \
         }                                                                                        \
     } while (0)
+
+// ---- LSX_BOUNDS_CHECK build (the pool refuses compute-sanitizer: profiles/r6d_compute_sanitizer_refused.txt) ------
+// -DLSX_BOUNDS_CHECK=1 turns every data-dependent index of the binning / list / record structures into a checked access:
+// an out-of-range index prints its site and traps (the launch then fails and the C ABI returns an error).  The default build
+// compiles the checks away.  tools/ab_variants.py builds the checked library; the GPU test tier is run through it once per
+// round (profiles/r6i_bounds_check_run.log).
+#ifndef LSX_BOUNDS_CHECK
+#define LSX_BOUNDS_CHECK 0
+#endif
+#if LSX_BOUNDS_CHECK
+#define LSX_CHECK_INDEX(i, n, what)                                                                              \
+    do {                                                                                                         \
+        if (!((unsigned long long)(i) < (unsigned long long)(n))) {                                              \
+            printf("LSX_BOUNDS_CHECK: %s index %lld outside [0, %lld) at %s:%d (block %d thread %d)\n", what,    \
+                   (long long)(i), (long long)(n), __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x);       \
+            __trap();                                                                                            \
+        }                                                                                                        \
+    } while (0)
+#else
+#define LSX_CHECK_INDEX(i, n, what) ((void)0)
+#endif
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
                                                               const float* __restrict__ records, int rec_stride,
                                                               uint32_t grid_x, uint8_t* __restrict__ masks,
                                                               uint32_t* __restrict__ blk_list, size_t list_stride,
-                                                              uint32_t* __restrict__ blk_cnt) {
+                                                              uint32_t* __restrict__ blk_cnt, int chk_points) {
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ uint32_t s_cnt[2][8][8];  // [chunk parity][warp][block]: double-buffered, one barrier per chunk
     const int tile = blockIdx.x;
@@ -106,7 +106,12 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
     uint32_t run = 0;  // lanes 0..7 (of every warp): entries of block `lane` emitted by earlier chunks
     // software pipeline over the 256-entry chunks: the record head of chunk c + 1 and the Gaussian index of chunk c + 2
     // are in flight while chunk c is classified and compacted (the two loads are dependent: index -> record)
-    auto load_id = [&](uint32_t i) -> uint32_t { return i < n ? __ldg(point_list + r.x + i) : 0u; };
+    auto load_id = [&](uint32_t i) -> uint32_t {
+        if (i < n) LSX_CHECK_INDEX((long long)r.x + i, list_stride, "tile list slot");
+        const uint32_t id = i < n ? __ldg(point_list + r.x + i) : 0u;
+        LSX_CHECK_INDEX(id, chk_points, "Gaussian id of a list entry");
+        return id;
+    };
     float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
     float2 h1 = make_float2(0.f, 0.f);
     {
@@ -158,7 +163,10 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
 #pragma unroll
         for (int w = 0; w < 8; ++w) {
             const uint32_t b0 = __shfl_sync(kFull, wbase, w);
-            if ((m >> w) & 1u) blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal[w] & lt)] = i;
+            if ((m >> w) & 1u) {
+                LSX_CHECK_INDEX(b0 + __popc(bal[w] & lt), n, "block list write");
+                blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal[w] & lt)] = i;
+            }
         }
         h0 = nh0;
         h1 = nh1;
@@ -170,10 +178,10 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
 
 int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,
                            int rec_stride, uint32_t grid_x, uint8_t* masks, uint32_t* blk_list, size_t list_stride,
-                           uint32_t* blk_cnt, cudaStream_t stream, bool debug) {
+                           uint32_t* blk_cnt, int num_points, cudaStream_t stream, bool debug) {
     if (num_tiles <= 0) return 0;
     footprint_masks_kernel<<<num_tiles, 256, 0, stream>>>(ranges, point_list, records, rec_stride, grid_x, masks, blk_list,
-                                                         list_stride, blk_cnt);
+                                                         list_stride, blk_cnt, num_points);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

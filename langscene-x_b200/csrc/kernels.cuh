@@ -109,13 +109,14 @@ int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, i
                        bool debug);
 int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* records,
                            int rec_stride, uint32_t grid_x, uint8_t* masks, uint32_t* blk_list, size_t list_stride,
-                           uint32_t* blk_cnt, cudaStream_t stream, bool debug);
+                           uint32_t* blk_cnt, int num_points, cudaStream_t stream, bool debug);
 int launch_debug_keys(int num_tiles, const uint2* ranges, const uint32_t* point_list, const float* depths,
                       uint64_t* keys_out, cudaStream_t stream);
 
 // ---- tile renderers (render_fwd.cu / render_bwd.cu) --------------------------------------------
 struct RenderParams {
     int W, H;
+    int P, R;  // Gaussians, list slots (capacity) — read by the LSX_BOUNDS_CHECK build only
     uint32_t grid_x, grid_y;
     float focal_x, focal_y;
     int F, Fi;  // feature widths (0 when include_feature is false)

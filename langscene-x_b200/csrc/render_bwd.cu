@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
 
     // back to front over the compacted list: round r covers elements n_eff-1 - (16 r + slot)
     stage.start(smem_raw, p.blk_list + (size_t)warp * p.list_stride + range.x, p.point_list + range.x, p.records,
-                n_eff - 1, -1, n_eff);
+                n_eff - 1, -1, n_eff, n, p.P);
+    LSX_CHECK_INDEX(cnt, (long long)n + 1, "block list length");
+    LSX_CHECK_INDEX((long long)range.y - 1, p.R, "tile range end");
     for (int r = 0; r < nrounds; ++r) {
         stage.advance(r);
         const int m = stage.round_size(r);
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
                     cg[ps][3] += wq.w * gT[ps][4 * q4 + 3];
                 }
             }
+            LSX_CHECK_INDEX(lds32i(ia), p.P, "gradient record");
             float* grec = p.grad_records + (size_t)lds32i(ia) * GS;
 #pragma unroll
             for (int ps = 0; ps < NPASS; ++ps) {

@@ -64,7 +64,9 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     Stage stage;
     const bool any_live = !__all_sync(kFull, T == 0.0f);
     if (nrounds > 0 && any_live) {
-        stage.start(smem_raw, list, p.point_list + range.x, p.records, 0, 1, cnt);
+        LSX_CHECK_INDEX(cnt, (long long)(range.y - range.x) + 1, "block list length");
+        LSX_CHECK_INDEX((long long)range.y - 1, p.R, "tile range end");
+        stage.start(smem_raw, list, p.point_list + range.x, p.records, 0, 1, cnt, (int)(range.y - range.x), p.P);
         for (int r = 0; r < nrounds; ++r) {
             stage.advance(r);
             const int m = stage.round_size(r);

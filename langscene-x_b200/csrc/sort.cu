@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
         const uint32_t k = s_key[j];
         const uint32_t d = (k >> shift) & mask;
         const uint32_t pos = s_gbase[d] + ((uint32_t)j - s_lstart[d]);
+        LSX_CHECK_INDEX(pos, n, "radix scatter destination");
         keys_out[pos] = k;
         vals_out[pos] = s_val[j];
     }

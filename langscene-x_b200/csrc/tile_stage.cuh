@@ -100,14 +100,17 @@ struct ListStage {
     const uint32_t* plist;   // point_list + range.x (positions are relative to the tile's range)
     const float* records;
     int first, dir, count;
+    int chk_range, chk_points;  // LSX_BOUNDS_CHECK: length of the tile's range, number of Gaussians
     uint32_t id_next, pos_next;  // id of this lane's element of round cur + 1, position of its element of round cur + 2
 
     __device__ __forceinline__ uint32_t load_pos(int q) const {
         const int t = q * CHUNK + (int)threadIdx.x;
+        if (threadIdx.x < CHUNK && t < count) LSX_CHECK_INDEX(first + dir * t, chk_range, "block list element");
         return (threadIdx.x < CHUNK && t < count) ? __ldg(list + (first + dir * t)) : 0u;
     }
     __device__ __forceinline__ uint32_t load_id(uint32_t pos, int q) const {
         const int t = q * CHUNK + (int)threadIdx.x;
+        if (threadIdx.x < CHUNK && t < count) LSX_CHECK_INDEX(pos, chk_range, "tile list position");
         return (threadIdx.x < CHUNK && t < count) ? __ldg(plist + pos) : 0u;
     }
     __device__ __forceinline__ int round_size(int q) const {
@@ -123,6 +126,7 @@ struct ListStage {
         const int slot = (int)(lane >> 1);
         const uint32_t id_s = __shfl_sync(kFullMask, id, slot);
         if (slot < m) {
+            LSX_CHECK_INDEX(id_s, chk_points, "Gaussian id of a list entry");
             const uint32_t piece = (lane & 1u) * (uint32_t)(kPerLane * 16);
             const char* src = reinterpret_cast<const char*>(records + (size_t)id_s * RS) + piece;
             const uint32_t dst = sbase + buf * (uint32_t)kBufBytes + (uint32_t)slot * (uint32_t)kRecBytes + piece;
@@ -133,7 +137,10 @@ struct ListStage {
     }
     // all 32 threads; the record buffers must be free (not aliased by live data) from here on
     __device__ __forceinline__ void start(unsigned char* smem, const uint32_t* list_, const uint32_t* plist_,
-                                          const float* records_, int first_, int dir_, int count_) {
+                                          const float* records_, int first_, int dir_, int count_, int range_len = 0x7fffffff,
+                                          int points = 0x7fffffff) {
+        chk_range = range_len;
+        chk_points = points;
         sbase = smem_u32(smem);
         list = list_;
         plist = plist_;
