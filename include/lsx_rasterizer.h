@@ -99,6 +99,16 @@ typedef struct lsx_forward_args {
      * waits for the (long finished) scan: the stream never drains.  If the hint turns out too small, binning and render are
      * repeated with the exact size before the call returns — outputs and *num_rendered are always those of the exact path. */
     int32_t binning_capacity_hint;
+    /* ABI v5 — fused render-wrapper mode ("activations, all_map construction ... pose transform" folded
+     * into the per-Gaussian kernels).  With raw_params != 0 the arrays means3D / scales / rotations / opacities hold the
+     * reference's RAW nn.Parameters (positions, log-scales, un-normalised quaternions, opacity logits;
+     * field_construction/scene/gaussian_model.py:193-213), all_map and cov3D_precomp must be NULL, and the preprocess kernel
+     * itself applies the optional camera pose (`pose`: 7 floats [quaternion | translation], NULL = none;
+     * gaussian_renderer/__init__.py:79-87), exp / normalize / sigmoid, the plane normal and the all_map row
+     * (gaussian_renderer/__init__.py:188-196) — what lsx_pose_transform_forward + lsx_gaussian_head_forward compute in two
+     * extra passes over P.  Outputs are unchanged. */
+    int32_t raw_params;
+    const float* pose;
 } lsx_forward_args;
 
 /* Returns 0 and stores the number of (Gaussian,tile) duplicates in *num_rendered.
@@ -159,6 +169,16 @@ typedef struct lsx_backward_args {
     /* ABI v5: size in bytes of the binning buffer the forward call allocated through binning_alloc (its list capacity is
      * recovered from it); 0 = the forward call ran without a capacity hint (capacity = R rounded up to 64). */
     uint64_t binning_bytes;
+    /* ABI v5 — fused render-wrapper mode, backward (the forward call must have used the same raw_params / pose).  The inputs
+     * means3D / scales / rotations are the RAW parameters; dL_dmeans3D, dL_dscales, dL_drotations and dL_dopacity receive the
+     * gradients of the RAW parameters (the chain rule through activations, plane normal, all_map and the pose transform is
+     * applied in the per-Gaussian kernel: what lsx_gaussian_head_backward + lsx_pose_transform_backward compute in two extra
+     * passes); dL_dcov3D and dL_dall_map may be NULL (not written).  dL_dpose (7 floats, may be NULL) receives the pose
+     * gradient — added to its contents when accumulate_pose != 0. */
+    int32_t raw_params;
+    const float* pose;
+    float* dL_dpose;
+    int32_t accumulate_pose;
 } lsx_backward_args;
 
 #define LSX_ACC_MEANS3D 0x001

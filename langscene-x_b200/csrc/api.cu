@@ -105,6 +105,7 @@ struct GeomScratch {
     uint32_t* total;
     void* sort_temp;
     void* scan_temp;
+    float* pose_partials;  // raw mode backward: one row of 16 pose-gradient partial sums per preprocess block
     size_t bytes;
     lsx_scratch_layout lay;
 };
@@ -131,6 +132,7 @@ GeomScratch carve_geom(char* base, int P, int rec_stride) {
     g.total = c.take<uint32_t>(64);
     g.sort_temp = c.take<char>(radix_sort_temp_bytes(P));
     g.scan_temp = c.take<char>(scan_temp_bytes(P));
+    g.pose_partials = c.take<float>((size_t)ceil_div(P > 0 ? P : 1, LSX_PRE_BWD_THREADS) * 16);
     g.bytes = c.total();
     g.lay.geom_bytes = g.bytes;
     return g;
@@ -344,8 +346,12 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
         (!a->cov3D_precomp && (!a->scales || !a->rotations)) ||
         (a->include_feature && (!a->language_feature || !a->language_feature_instance || !a->out_language_feature ||
                                 !a->out_language_feature_instance)) ||
-        (a->render_geo && !a->all_map)) {
+        (a->render_geo && !a->all_map && !a->raw_params)) {
         set_error("lsx_rasterize_forward: a required input pointer is null");
+        return -1;
+    }
+    if (a->raw_params && (a->cov3D_precomp || a->all_map || !a->scales || !a->rotations)) {
+        set_error("lsx_rasterize_forward: raw_params needs scales + rotations and takes neither cov3D_precomp nor all_map");
         return -1;
     }
     if (!a->colors_precomp && a->M < (a->D + 1) * (a->D + 1)) {
@@ -383,6 +389,7 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
     pp.scale_modifier = a->scale_modifier;
     pp.prefiltered = a->prefiltered; pp.render_geo = a->render_geo; pp.include_feature = a->include_feature;
     pp.rec_stride = rs; pp.n_channels = nch;
+    pp.raw_params = a->raw_params; pp.pose = a->raw_params ? a->pose : nullptr;
     pp.means3D = a->means3D; pp.scales = a->scales; pp.rotations = a->rotations; pp.opacities = a->opacities;
     pp.shs = a->shs; pp.cov3D_precomp = a->cov3D_precomp; pp.colors_precomp = a->colors_precomp;
     pp.language_feature = a->language_feature; pp.language_feature_instance = a->language_feature_instance;
@@ -549,7 +556,8 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     }
     if (!a->geom_buffer || !a->image_buffer || (R > 0 && !a->binning_buffer) || !a->radii || !a->means3D ||
         !a->dL_dout_color || !a->dL_dmeans2D || !a->dL_dmeans2D_abs || !a->dL_dconic || !a->dL_dopacity ||
-        !a->dL_dcolors || !a->dL_dmeans3D || !a->dL_dcov3D || !a->dL_dscales || !a->dL_drotations || !a->dL_dall_map ||
+        !a->dL_dcolors || !a->dL_dmeans3D || (!a->dL_dcov3D && !a->raw_params) || !a->dL_dscales || !a->dL_drotations ||
+        (!a->dL_dall_map && !a->raw_params) ||
         (a->M > 0 && !a->dL_dsh) ||
         (a->include_feature && (!a->dL_dout_language_feature || !a->dL_dout_language_feature_instance ||
                                 !a->dL_dlanguage_feature || !a->dL_dlanguage_feature_instance)) ||
@@ -613,6 +621,12 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     bp.grad_records = gm.grad_records; bp.grad_stride = gs; bp.n_channels_pad = round_up4(nch);
     bp.F = F; bp.Fi = Fi; bp.include_feature = a->include_feature; bp.render_geo = a->render_geo;
     bp.accumulate = a->accumulate_param_grads;
+    bp.raw_params = a->raw_params; bp.pose = a->raw_params ? a->pose : nullptr; bp.conic_opacity = gm.conic_opacity;
+    bp.pose_partials = gm.pose_partials; bp.dL_dpose = a->dL_dpose; bp.accumulate_pose = a->accumulate_pose;
+    if (a->raw_params && (a->cov3D_precomp || !a->scales || !a->rotations)) {
+        set_error("lsx_rasterize_backward: raw_params needs scales + rotations and no cov3D_precomp");
+        return -1;
+    }
     bp.geo_scale_x = 0.5f * (float)W; bp.geo_scale_y = 0.5f * (float)H;
     bp.dL_dmean2D = a->dL_dmeans2D; bp.dL_dmean2D_abs = a->dL_dmeans2D_abs; bp.dL_dconic = a->dL_dconic;
     bp.dL_dopacity = a->dL_dopacity; bp.dL_dcolor = a->dL_dcolors;

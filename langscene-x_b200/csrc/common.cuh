@@ -8,6 +8,9 @@
 
 namespace lsx {
 
+#ifndef LSX_PRE_BWD_THREADS
+#define LSX_PRE_BWD_THREADS 128  // Gaussians per block of the preprocess backward kernel (also sizes its pose-partial rows)
+#endif
 constexpr int TILE_X = 16;  // tile geometry is part of the binning contract (config.h:19-20 in the reference)
 constexpr int TILE_Y = 16;
 constexpr int TILE_PIXELS = TILE_X * TILE_Y;

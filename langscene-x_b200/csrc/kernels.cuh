@@ -12,6 +12,8 @@ struct PreprocessFwdParams {
     uint32_t grid_x, grid_y;
     float focal_x, focal_y, tan_fovx, tan_fovy, scale_modifier;
     int prefiltered, render_geo, include_feature;
+    int raw_params;     // fused render-wrapper mode: raw parameters in, activations / plane normal / all_map computed in-kernel
+    const float* pose;  // raw mode: optional camera pose [quaternion | translation] (7 floats, device)
     int rec_stride;
     int n_channels;  // blended channels: 3 + F + Fi + (render_geo ? 5 : 0)
     const float* means3D;
@@ -60,6 +62,14 @@ struct PreprocessBwdParams {
     int grad_stride;  // floats per record
     int n_channels_pad;  // round_up4(blended channels) = offset of the geometry terms inside a record
     int F, Fi, include_feature, render_geo;
+    // fused render-wrapper mode (see PreprocessFwdParams::raw_params): means3D / scales / rotations are the raw parameters, the
+    // activated opacity comes from the forward pass's conic_opacity; pose_partials: blocks x 16 floats of scratch
+    int raw_params;
+    const float* pose;
+    const float4* conic_opacity;
+    float* pose_partials;
+    float* dL_dpose;      // 7 floats
+    int accumulate_pose;  // dL_dpose += instead of =
     int accumulate;  // LSX_ACC_* bit mask: parameter gradients with out += value (multi-view accumulation) instead of out = value
     // the tile pass leaves the constant factors of the geometry terms (0.5 W / 0.5 H of the mean2D
     // terms, -0.5 of the conic terms) to this kernel, which applies them once per Gaussian instead of once per visit
@@ -82,6 +92,8 @@ struct PreprocessBwdParams {
 
 int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, bool debug);
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug);
+// pose.cu: d_pose (7) from `rows` x 16 partial sums (fixed-order sum in double, chain rule through R(q / |q|))
+int launch_pose_finish(int rows, const float* pose, const float* partials, float* d_pose, int accumulate, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t stream);
 
 // ---- device-wide primitives (sort.cu) ---------------------------------------------------------

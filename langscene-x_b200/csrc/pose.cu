@@ -16,35 +16,14 @@
 // and a one-block epilogue adds the partials in a fixed order (deterministic) and applies the chain rule through R(q/|q|) in
 // double precision.  The masked L1 does the same with per-block partial sums; no atomics anywhere.
 #include "../../include/lsx_rasterizer.h"
+#include "head_math.cuh"
 #include "kernels.cuh"
 
 namespace lsx {
 namespace {
 
-constexpr int kPoseTerms = 16;
 constexpr int kPoseBlocks = 148 * 4;   // partial rows: one per block of the backward grid (grid-stride over P)
 constexpr int kL1Blocks = 148 * 8;
-
-struct Rot3 {
-    float m[3][3];
-};
-
-__device__ __forceinline__ Rot3 rotation_of(const float* __restrict__ pose) {
-    const float a = pose[0], b = pose[1], c = pose[2], d = pose[3];
-    const float n = sqrtf(a * a + b * b + c * c + d * d);
-    const float r = a / n, x = b / n, y = c / n, z = d / n;
-    Rot3 R;
-    R.m[0][0] = 1.f - 2.f * (y * y + z * z);
-    R.m[0][1] = 2.f * (x * y - r * z);
-    R.m[0][2] = 2.f * (x * z + r * y);
-    R.m[1][0] = 2.f * (x * y + r * z);
-    R.m[1][1] = 1.f - 2.f * (x * x + z * z);
-    R.m[1][2] = 2.f * (y * z - r * x);
-    R.m[2][0] = 2.f * (x * z - r * y);
-    R.m[2][1] = 2.f * (y * z + r * x);
-    R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-    return R;
-}
 
 __global__ void __launch_bounds__(256) pose_fwd_kernel(const int P, const float* __restrict__ pose, const float* __restrict__ xyz,
                                                        const float* __restrict__ rot, float* __restrict__ out_xyz,
@@ -127,16 +106,19 @@ __global__ void __launch_bounds__(256) pose_bwd_kernel(const int P, const float*
     }
 }
 
-// one block: fixed-order sum of the block partials (double), then the chain rule through R(q / |q|)
-__global__ void __launch_bounds__(32) pose_bwd_finish_kernel(const int nblocks, const float* __restrict__ pose,
-                                                             const float* __restrict__ partials, float* __restrict__ d_pose) {
+// one block of 16 warps: warp k adds term k of the partial rows (every lane a strided subset in double, then a fixed shuffle
+// tree: deterministic), thread 0 applies the chain rule through R(q / |q|)
+__global__ void __launch_bounds__(512) pose_bwd_finish_kernel(const int nblocks, const float* __restrict__ pose,
+                                                              const float* __restrict__ partials, float* __restrict__ d_pose,
+                                                              const int accumulate) {
     __shared__ double s[kPoseTerms];
-    if (threadIdx.x < kPoseTerms) {
-        double v = 0.0;
-        for (int b = 0; b < nblocks; ++b) v += (double)partials[b * kPoseTerms + threadIdx.x];
-        s[threadIdx.x] = v;
-    }
-    __syncwarp();
+    const int lane = threadIdx.x & 31, term = threadIdx.x >> 5;
+    double v = 0.0;
+    for (int b = lane; b < nblocks; b += 32) v += (double)partials[(size_t)b * kPoseTerms + term];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s[term] = v;
+    __syncthreads();
     if (threadIdx.x != 0) return;
     const double a = pose[0], b = pose[1], c = pose[2], d = pose[3];
     const double n = sqrt(a * a + b * b + c * c + d * d);
@@ -147,13 +129,9 @@ __global__ void __launch_bounds__(32) pose_bwd_finish_kernel(const int nblocks, 
     const double gy = 2.0 * (-2.0 * y * D00 + x * D01 + r * D02 + x * D10 + z * D12 - r * D20 + z * D21 - 2.0 * y * D22);
     const double gz = 2.0 * (-2.0 * z * D00 - r * D01 + x * D02 + r * D10 - 2.0 * z * D11 + y * D12 + x * D20 + y * D21);
     const double dot = gr * r + gx * x + gy * y + gz * z;  // d(q/|q|)/dq = (I - qn qn^T) / |q|
-    d_pose[0] = (float)((gr - dot * r) / n + s[12]);
-    d_pose[1] = (float)((gx - dot * x) / n + s[13]);
-    d_pose[2] = (float)((gy - dot * y) / n + s[14]);
-    d_pose[3] = (float)((gz - dot * z) / n + s[15]);
-    d_pose[4] = (float)s[9];
-    d_pose[5] = (float)s[10];
-    d_pose[6] = (float)s[11];
+    const double out[7] = {(gr - dot * r) / n + s[12], (gx - dot * x) / n + s[13], (gy - dot * y) / n + s[14],
+                           (gz - dot * z) / n + s[15], s[9], s[10], s[11]};
+    for (int k = 0; k < 7; ++k) d_pose[k] = (float)(out[k] + (accumulate ? (double)d_pose[k] : 0.0));
 }
 
 // ---- masked L1 ------------------------------------------------------------------------------------------------------
@@ -194,6 +172,13 @@ __global__ void __launch_bounds__(256) masked_l1_bwd_kernel(const long long n, c
 }
 
 }  // namespace
+
+int launch_pose_finish(int rows, const float* pose, const float* partials, float* d_pose, int accumulate, cudaStream_t stream) {
+    pose_bwd_finish_kernel<<<1, 512, 0, stream>>>(rows, pose, partials, d_pose, accumulate);
+    LSX_KERNEL_OK(stream, false);
+    return 0;
+}
+
 }  // namespace lsx
 
 using namespace lsx;
@@ -227,9 +212,7 @@ extern "C" int lsx_pose_transform_backward(int32_t P, const float* pose, const f
     pose_bwd_kernel<<<blocks, 256, 0, stream>>>(P, pose, xyz, rotation_raw, dL_dmeans3D, dL_drotations, dL_dxyz,
                                                 dL_drotation_raw, partials);
     LSX_KERNEL_OK(stream, false);
-    pose_bwd_finish_kernel<<<1, 32, 0, stream>>>(blocks, pose, partials, dL_dpose);
-    LSX_KERNEL_OK(stream, false);
-    return 0;
+    return launch_pose_finish(blocks, pose, partials, dL_dpose, 0, stream);
 }
 
 extern "C" int32_t lsx_masked_l1_num_blocks(int64_t n) {

@@ -19,6 +19,7 @@
 //   * arithmetic that feeds radii / tile rects / depth keys keeps the reference's scalar expression
 //     order (including the fp64 island in ndc_to_pix) because those outputs are compared bit-exactly.
 #include "coalesce.cuh"
+#include "head_math.cuh"
 #include "kernels.cuh"
 
 namespace lsx {
@@ -121,6 +122,12 @@ __host__ __device__ static inline int record_tile_row(int rec_stride) { return r
 
 // One Gaussian per thread.  `sh_row`: its SH coefficients in shared memory; `rec`: its row of the block's record
 // tile in shared memory, whose feature / map columns have already been filled cooperatively.
+// RAW = the fused render-wrapper mode: `means3D / scales / rotations / opacities` are the reference's raw
+// nn.Parameters (positions, log-scales, un-normalised quaternions, opacity logits), `all_map` is absent, and the wrapper's
+// per-Gaussian work — optional camera-pose transform, exp / normalize / sigmoid, plane normal, all_map (head_math.cuh) — is
+// done here instead of in separate passes over P.  It is a separate instantiation so that the code generated for the
+// reference-shaped mode (whose radii / rects / keys are a bit-exact contract) is untouched.
+template <bool RAW>
 __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p, const int idx, const float* __restrict__ sh_row,
                                                    float* __restrict__ rec) {
     // defaults for a culled splat (its record is never read; keep it finite)
@@ -128,12 +135,27 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
     reinterpret_cast<float4*>(rec)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     rec[REC_HEAD + 0] = rec[REC_HEAD + 1] = rec[REC_HEAD + 2] = 0.f;
     for (int c = p.n_channels; c < p.rec_stride - REC_HEAD; ++c) rec[REC_HEAD + c] = 0.f;
+    if constexpr (RAW) {
+        if (p.render_geo)  // the map columns are produced below; a culled splat keeps zeros
+            for (int c = 0; c < 5; ++c) rec[REC_HEAD + 3 + (p.include_feature ? p.F + p.Fi : 0) + c] = 0.f;
+    }
     p.radii[idx] = 0;
     p.tiles_touched[idx] = 0;
     p.out_observe[idx] = 0;
     p.depth_keys[idx] = 0xFFFFFFFFu;
 
-    const float3 pw = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    float3 pw = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    float4 q_in = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (RAW) {
+        q_in = reinterpret_cast<const float4*>(p.rotations)[idx];
+        if (p.pose != nullptr) {  // render(..., camera_pose=pose): means3D = R xyz + T, rotations = pose_q (x) rotation
+            const Rot3 Rp = rotation_of(p.pose);
+            float xw[3];
+            pose_apply_point(Rp, p.pose, pw.x, pw.y, pw.z, xw);
+            pw = make_float3(xw[0], xw[1], xw[2]);
+            q_in = pose_apply_quat(p.pose, q_in);
+        }
+    }
     const float3 pv = xform_point_4x3(pw, p.view);
     if (pv.z <= 0.2f) {
         if (p.prefiltered) {
@@ -148,7 +170,22 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
     const float3 pn = make_float3(ph.x * pw_inv, ph.y * pw_inv, ph.z * pw_inv);
 
     float cov6[6];
-    if (p.cov3D_precomp != nullptr) {
+    float raw_opacity = 0.f;  // RAW: sigmoid of the logit
+    if constexpr (RAW) {
+        const HeadCam hc = load_cam(p.view, p.campos);
+        const float xw[3] = {pw.x, pw.y, pw.z};
+        const float sraw[3] = {p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]};
+        const HeadFrame hf = head_frame(hc, xw, sraw, q_in, p.opacities[idx]);
+        raw_opacity = hf.sig;
+        if (p.render_geo) {  // all_map = [local plane normal, 1, |<normal, camera-space position>|]
+            float* am = rec + REC_HEAD + 3 + (p.include_feature ? p.F + p.Fi : 0);
+            am[0] = hf.nl[0]; am[1] = hf.nl[1]; am[2] = hf.nl[2]; am[3] = 1.0f; am[4] = fabsf(hf.d);
+        }
+        world_covariance(make_float3(hf.sc[0], hf.sc[1], hf.sc[2]), p.scale_modifier, make_float4(hf.q[0], hf.q[1], hf.q[2], hf.q[3]),
+                         cov6);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) p.cov3D[6 * idx + i] = cov6[i];
+    } else if (p.cov3D_precomp != nullptr) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) cov6[i] = p.cov3D_precomp[6 * idx + i];
     } else {
@@ -257,7 +294,7 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
         for (int c = 0; c < 3; ++c) rgb[c] = p.colors_precomp[3 * idx + c];
     }
 
-    const float opacity = p.opacities[idx];
+    const float opacity = RAW ? raw_opacity : p.opacities[idx];
     p.depths[idx] = pv.z;
     p.depth_keys[idx] = __float_as_uint(pv.z);
     p.radii[idx] = (int)my_radius;
@@ -276,6 +313,7 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
 // Block = 128 Gaussians.  SH coefficients in, and the packed blend records out, move through shared memory with
 // coalesced 16-B accesses (coalesce.cuh); language / instance features and the all_map rows are copied
 // cooperatively straight into their columns of the record tile.
+template <bool RAW>
 __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const PreprocessFwdParams p) {
     extern __shared__ __align__(16) float s_pre[];
     const int n_sh = p.M * 3;
@@ -293,10 +331,10 @@ __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const Pr
         slab_load<kPreFwdThreads>(s_rec + c, p.language_feature_instance + (size_t)b0 * p.Fi, rows, p.Fi, rec_row);
         c += p.Fi;
     }
-    if (p.render_geo) slab_load<kPreFwdThreads>(s_rec + c, p.all_map + (size_t)b0 * 5, rows, 5, rec_row);
+    if (!RAW && p.render_geo) slab_load<kPreFwdThreads>(s_rec + c, p.all_map + (size_t)b0 * 5, rows, 5, rec_row);
     __syncthreads();
     if ((int)threadIdx.x < rows)
-        preprocess_fwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_stride, s_rec + threadIdx.x * rec_row);
+        preprocess_fwd_row<RAW>(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_stride, s_rec + threadIdx.x * rec_row);
     __syncthreads();
     slab_store<kPreFwdThreads>(p.records + (size_t)b0 * p.rec_stride, s_rec, rows, p.rec_stride, rec_row);
 }
@@ -310,8 +348,14 @@ __global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const Pr
 // Culled splats have an all-zero record (memset, never accumulated into).
 constexpr int kPreBwdThreads = LSX_PRE_BWD_THREADS;
 
+// RAW (see preprocess_fwd_row): the inputs are the raw parameters; the gradients of the activated scale / rotation / opacity /
+// position and of the all_map row are NOT written but pushed on through the wrapper's backward (head_math.cuh: activations,
+// plane normal, all_map, optional camera pose) and arrive in dL_dmeans3D / dL_dscales / dL_drotations / dL_dopacity as
+// gradients of the RAW parameters; `pose_acc` collects this row's 16 pose-gradient terms.
+template <bool RAW>
 __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, float* __restrict__ sh_row,
-                                                   const float (&grec)[3], const float (&ggeo)[8]) {
+                                                   const float (&grec)[3], const float (&ggeo)[8], const float (&gmap)[5],
+                                                   float (&pose_acc)[kPoseTerms]) {
     const int n_sh = p.M * 3;
     float* g_sh = p.dL_dsh ? sh_row : nullptr;
     p.dL_dmean2D[3 * idx + 0] = ggeo[0];
@@ -324,15 +368,18 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
     // p.accumulate: bit mask of the outputs that are ADDED to (multi-view accumulation) instead of written
     const unsigned am = (unsigned)p.accumulate;
     auto put = [am](float* dst, const float v, const unsigned bit) { *dst = (am & bit) ? *dst + v : v; };
-    put(p.dL_dopacity + idx, ggeo[7], LSX_ACC_OPACITY);
+    if constexpr (!RAW) put(p.dL_dopacity + idx, ggeo[7], LSX_ACC_OPACITY);
 
     if (!(p.radii[idx] > 0)) {
+        if constexpr (RAW) {
+            if (!(am & LSX_ACC_OPACITY)) p.dL_dopacity[idx] = 0.f;
+        }
         // culled splat: every gradient row is zero (the reference relies on torch::zeros for this)
         if (!(am & LSX_ACC_MEANS3D)) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p.dL_dmeans3D[3 * idx + i] = 0.f;
         }
-        if (!(am & LSX_ACC_COV3D)) {
+        if (!(am & LSX_ACC_COV3D) && p.dL_dcov3D != nullptr) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) p.dL_dcov3D[6 * idx + i] = 0.f;
         }
@@ -346,7 +393,29 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         return;
     }
 
-    const float3 mean = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    float3 mean = make_float3(p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]);
+    // RAW: redo the wrapper's forward for this row (pose transform, activations, plane normal)
+    const float3 xyz_raw = mean;
+    float4 q_raw = make_float4(0.f, 0.f, 0.f, 0.f), q_in = q_raw;
+    HeadCam hc;
+    HeadFrame hf;
+    Rot3 Rp;
+    if constexpr (RAW) {
+        q_raw = reinterpret_cast<const float4*>(p.rotations)[idx];
+        q_in = q_raw;
+        if (p.pose != nullptr) {
+            Rp = rotation_of(p.pose);
+            float xw[3];
+            pose_apply_point(Rp, p.pose, mean.x, mean.y, mean.z, xw);
+            mean = make_float3(xw[0], xw[1], xw[2]);
+            q_in = pose_apply_quat(p.pose, q_raw);
+        }
+        hc = load_cam(p.view, p.campos);
+        const float xw2[3] = {mean.x, mean.y, mean.z};
+        const float sraw[3] = {p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]};
+        hf = head_frame(hc, xw2, sraw, q_in, 0.f);
+        hf.sig = p.conic_opacity[idx].w;  // the activated opacity the forward pass stored (visible splats only)
+    }
     const float* cov6 = (p.cov3D_precomp ? p.cov3D_precomp : p.cov3D) + 6 * (size_t)idx;
     float c6[6];
 #pragma unroll
@@ -391,7 +460,8 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < 6; ++i) g_cov[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) put(p.dL_dcov3D + 6 * idx + i, g_cov[i], LSX_ACC_COV3D);
+    for (int i = 0; i < 6; ++i)
+        if (!RAW || p.dL_dcov3D != nullptr) put(p.dL_dcov3D + 6 * idx + i, g_cov[i], LSX_ACC_COV3D);
 
     // gradient w.r.t. the upper 2x3 block of T
     float tv0[3], tv1[3];  // (row of T) . V columns
@@ -532,14 +602,19 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
     }
 
-    put(p.dL_dmeans3D + 3 * idx + 0, g_mean.x, LSX_ACC_MEANS3D);
-    put(p.dL_dmeans3D + 3 * idx + 1, g_mean.y, LSX_ACC_MEANS3D);
-    put(p.dL_dmeans3D + 3 * idx + 2, g_mean.z, LSX_ACC_MEANS3D);
+    if constexpr (!RAW) {
+        put(p.dL_dmeans3D + 3 * idx + 0, g_mean.x, LSX_ACC_MEANS3D);
+        put(p.dL_dmeans3D + 3 * idx + 1, g_mean.y, LSX_ACC_MEANS3D);
+        put(p.dL_dmeans3D + 3 * idx + 2, g_mean.z, LSX_ACC_MEANS3D);
+    }
 
     // ---- part 4: world covariance -> scale / rotation (backward.cu:278-341) ------------------------
+    float g_sc[3] = {0.f, 0.f, 0.f};                     // RAW: dL/d(activated scale), dL/d(normalised quaternion)
+    float4 g_qn = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.scales != nullptr) {
-        const float3 sc = make_float3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
-        const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+        const float3 sc = RAW ? make_float3(hf.sc[0], hf.sc[1], hf.sc[2])
+                              : make_float3(p.scales[3 * idx], p.scales[3 * idx + 1], p.scales[3 * idx + 2]);
+        const float4 q = RAW ? make_float4(hf.q[0], hf.q[1], hf.q[2], hf.q[3]) : reinterpret_cast<const float4*>(p.rotations)[idx];
         const float r = q.x, x = q.y, y = q.z, z = q.w;
         Mat3 R;
         R.m[0][0] = 1.f - 2.f * (y * y + z * z);
@@ -576,12 +651,12 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         const Mat3 Rt = mat3_transpose(R);
         Mat3 gMt = mat3_transpose(gM);
 
-        put(p.dL_dscales + 3 * idx + 0, Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2],
-            LSX_ACC_SCALES);
-        put(p.dL_dscales + 3 * idx + 1, Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2],
-            LSX_ACC_SCALES);
-        put(p.dL_dscales + 3 * idx + 2, Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2],
-            LSX_ACC_SCALES);
+        g_sc[0] = Rt.m[0][0] * gMt.m[0][0] + Rt.m[0][1] * gMt.m[0][1] + Rt.m[0][2] * gMt.m[0][2];
+        if constexpr (!RAW) put(p.dL_dscales + 3 * idx + 0, g_sc[0], LSX_ACC_SCALES);
+        g_sc[1] = Rt.m[1][0] * gMt.m[1][0] + Rt.m[1][1] * gMt.m[1][1] + Rt.m[1][2] * gMt.m[1][2];
+        if constexpr (!RAW) put(p.dL_dscales + 3 * idx + 1, g_sc[1], LSX_ACC_SCALES);
+        g_sc[2] = Rt.m[2][0] * gMt.m[2][0] + Rt.m[2][1] * gMt.m[2][1] + Rt.m[2][2] * gMt.m[2][2];
+        if constexpr (!RAW) put(p.dL_dscales + 3 * idx + 2, g_sc[2], LSX_ACC_SCALES);
 
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
@@ -597,24 +672,54 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
                4 * y * (gMt.m[2][2] + gMt.m[0][0]);
         gq.w = 2 * r * (gMt.m[0][1] - gMt.m[1][0]) + 2 * x * (gMt.m[2][0] + gMt.m[0][2]) + 2 * y * (gMt.m[1][2] + gMt.m[2][1]) -
                4 * z * (gMt.m[1][1] + gMt.m[0][0]);
-        if (am & LSX_ACC_ROTATIONS) {
-            const float4 o = reinterpret_cast<const float4*>(p.dL_drotations)[idx];
-            gq = make_float4(gq.x + o.x, gq.y + o.y, gq.z + o.z, gq.w + o.w);
+        g_qn = gq;
+        if constexpr (!RAW) {
+            if (am & LSX_ACC_ROTATIONS) {
+                const float4 o = reinterpret_cast<const float4*>(p.dL_drotations)[idx];
+                gq = make_float4(gq.x + o.x, gq.y + o.y, gq.z + o.z, gq.w + o.w);
+            }
+            reinterpret_cast<float4*>(p.dL_drotations)[idx] = gq;  // w.r.t. the raw (un-normalised) quaternion
         }
-        reinterpret_cast<float4*>(p.dL_drotations)[idx] = gq;  // w.r.t. the raw (un-normalised) quaternion
-    } else {
+    } else if (!RAW) {
         if (!(am & LSX_ACC_SCALES)) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
         }
         if (!(am & LSX_ACC_ROTATIONS)) reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+
+    if constexpr (RAW) {
+        // ---- part 5: the render wrapper's backward (activations, plane normal, all_map, camera pose) ----
+        const float gm[3] = {g_mean.x, g_mean.y, g_mean.z};
+        const float gr[4] = {g_qn.x, g_qn.y, g_qn.z, g_qn.w};
+        const HeadGrads hg = head_backward_row(hc, hf, q_in, g_sc, gr, ggeo[7], gmap, gm);
+        float d_xyz[3] = {hg.xyz[0], hg.xyz[1], hg.xyz[2]};
+        float4 d_q = hg.qraw;
+        if (p.pose != nullptr) {
+            pose_backward_point(Rp, xyz_raw.x, xyz_raw.y, xyz_raw.z, hg.xyz[0], hg.xyz[1], hg.xyz[2], d_xyz, pose_acc);
+            d_q = pose_backward_quat(p.pose, q_raw, hg.qraw, pose_acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) put(p.dL_dmeans3D + 3 * idx + i, d_xyz[i], LSX_ACC_MEANS3D);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) put(p.dL_dscales + 3 * idx + i, hg.sraw[i], LSX_ACC_SCALES);
+        if (am & LSX_ACC_ROTATIONS) {
+            const float4 o = reinterpret_cast<const float4*>(p.dL_drotations)[idx];
+            d_q = make_float4(d_q.x + o.x, d_q.y + o.y, d_q.z + o.z, d_q.w + o.w);
+        }
+        reinterpret_cast<float4*>(p.dL_drotations)[idx] = d_q;
+        put(p.dL_dopacity + idx, hg.oraw, LSX_ACC_OPACITY);
+    }
 }
 
 // Block = 128 Gaussians.  The SH slab and the gradient-record slab of the block are moved through shared memory
 // with coalesced 16-B accesses (coalesce.cuh); dL/dsh and the unpacked colour / feature / map gradients leave the
 // same way.  Every output row is written exactly once (zeros for culled splats).
-__global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const PreprocessBwdParams p) {
+#ifndef LSX_PRE_BWD_RAW_MINBLOCKS
+#define LSX_PRE_BWD_RAW_MINBLOCKS 1
+#endif
+template <bool RAW>
+__global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_RAW_MINBLOCKS : 1) preprocess_bwd_kernel(const PreprocessBwdParams p) {
     extern __shared__ __align__(16) float s_pre[];
     const int n_sh = p.M * 3;
     const int sh_row = padded_row(n_sh);
@@ -625,9 +730,14 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
     const float* rec0 = p.grad_records + (size_t)b0 * p.grad_stride;
     // the thread's own colour gradient and 8 geometry terms, straight from its record (16-B aligned: both offsets are
     // multiples of 4 floats)
-    float gcol[3] = {0.f, 0.f, 0.f}, ggeo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float gcol[3] = {0.f, 0.f, 0.f}, ggeo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gmap[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     if ((int)threadIdx.x < rows) {
         const float* rec = rec0 + (size_t)threadIdx.x * p.grad_stride;
+        if (RAW && p.render_geo) {  // the all_map gradient goes on through the wrapper's backward instead of out
+            const int cm = 3 + (p.include_feature ? p.F + p.Fi : 0);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) gmap[k] = __ldg(rec + cm + k);
+        }
         const float4 c4 = __ldg(reinterpret_cast<const float4*>(rec));
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(rec + p.n_channels_pad));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(rec + p.n_channels_pad + 4));
@@ -650,13 +760,38 @@ __global__ void __launch_bounds__(kPreBwdThreads) preprocess_bwd_kernel(const Pr
                                           (am & LSX_ACC_INST) != 0);
         c += p.Fi;
     }
-    if (p.render_geo) {
+    if (RAW && p.dL_dall_map == nullptr) {
+        // raw mode: all_map is not an input of the call, its gradient is consumed by preprocess_bwd_row
+    } else if (p.render_geo) {
         slab_copy_columns<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, rec0, rows, 5, p.grad_stride, c, (am & LSX_ACC_ALL_MAP) != 0);
     } else if (!(am & LSX_ACC_ALL_MAP)) {
         for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
     }
     __syncthreads();
-    if ((int)threadIdx.x < rows) preprocess_bwd_row(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, gcol, ggeo);
+    float pose_acc[kPoseTerms];
+#pragma unroll
+    for (int k = 0; k < kPoseTerms; ++k) pose_acc[k] = 0.f;
+    if ((int)threadIdx.x < rows)
+        preprocess_bwd_row<RAW>(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, gcol, ggeo, gmap, pose_acc);
+    if (RAW && p.pose != nullptr && p.pose_partials != nullptr) {
+        // this block's row of pose-gradient partial sums (fixed order: deterministic); lsx::launch_pose_finish adds the rows
+        __shared__ float s_pose[kPreBwdThreads / 32][kPoseTerms];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < kPoseTerms; ++k) {
+            float v = pose_acc[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (lane == 0) s_pose[warp][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < kPoseTerms) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kPreBwdThreads / 32; ++w) v += s_pose[w][threadIdx.x];
+            p.pose_partials[(size_t)blockIdx.x * kPoseTerms + threadIdx.x] = v;
+        }
+    }
     __syncthreads();
     if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, (am & LSX_ACC_SH) != 0);
 }
@@ -676,7 +811,7 @@ __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* _
 // The opt-in dynamic shared-memory limit is a per-device attribute of the function: remember what has been set for
 // (kernel slot, device) so that a process driving several GPUs configures each of them (benign race: monotone maximum).
 static cudaError_t ensure_dynamic_smem(const void* func, size_t bytes, int slot) {
-    static size_t configured[2][64] = {};
+    static size_t configured[4][64] = {};
     if (bytes <= 48 * 1024) return cudaSuccess;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -695,8 +830,13 @@ int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, boo
     const int sh_stride = p.shs ? padded_row(n_sh) : 0;
     const size_t smem = ((size_t)((kPreFwdThreads * sh_stride + 3) & ~3) + (size_t)kPreFwdThreads * record_tile_row(p.rec_stride)) *
                         sizeof(float);
-    LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel), smem, 0));
-    preprocess_fwd_kernel<<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
+    if (p.raw_params) {
+        LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel<true>), smem, 2));
+        preprocess_fwd_kernel<true><<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
+    } else {
+        LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel<false>), smem, 0));
+        preprocess_fwd_kernel<false><<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
+    }
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
@@ -704,9 +844,20 @@ int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, boo
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
     const size_t smem = (size_t)kPreBwdThreads * (p.shs ? padded_row(p.M * 3) : 0) * sizeof(float);
-    LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel), smem, 1));
-    preprocess_bwd_kernel<<<ceil_div(p.P, kPreBwdThreads), kPreBwdThreads, smem, stream>>>(p);
-    LSX_KERNEL_OK(stream, debug);
+    const int blocks = ceil_div(p.P, kPreBwdThreads);
+    if (p.raw_params) {
+        LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel<true>), smem, 3));
+        preprocess_bwd_kernel<true><<<blocks, kPreBwdThreads, smem, stream>>>(p);
+        LSX_KERNEL_OK(stream, debug);
+        if (p.pose != nullptr && p.dL_dpose != nullptr) {
+            const int rc = launch_pose_finish(blocks, p.pose, p.pose_partials, p.dL_dpose, p.accumulate_pose, stream);
+            if (rc) return rc;
+        }
+    } else {
+        LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel<false>), smem, 1));
+        preprocess_bwd_kernel<false><<<blocks, kPreBwdThreads, smem, stream>>>(p);
+        LSX_KERNEL_OK(stream, debug);
+    }
     return 0;
 }
 

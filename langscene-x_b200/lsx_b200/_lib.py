@@ -33,6 +33,7 @@ class ForwardArgs(ctypes.Structure):
         ("image_alloc", ALLOC_FN), ("image_user", c_void_p),
         ("stream", c_void_p),
         ("binning_capacity_hint", c_int32),
+        ("raw_params", c_int32), ("pose", c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ class BackwardArgs(ctypes.Structure):
         ("stream", c_void_p),
         ("accumulate_param_grads", c_int32),
         ("binning_bytes", c_uint64),
+        ("raw_params", c_int32), ("pose", c_void_p), ("dL_dpose", c_void_p), ("accumulate_pose", c_int32),
     ]
 
 

@@ -4,9 +4,9 @@ configs 4 and 5) — the caller side of the rasterizer hot path.
 One step restates, for a BATCH of views sharded over the ranks of one node, what one iteration of the reference's loop
 (field_construction/gaussian_field.py:184-543) does for one view:
 
-    pose_transform (optim_pose, gaussian_renderer/__init__.py:79-87)          lsx_pose_transform_forward
-    activations + plane normal + all_map (gaussian_model.py:193-236,          lsx_gaussian_head_forward
-        gaussian_renderer/__init__.py:188-196)
+    pose_transform (optim_pose, gaussian_renderer/__init__.py:79-87)          } inside lsx_rasterize_forward's per-Gaussian kernel
+    activations + plane normal + all_map (gaussian_model.py:193-236,          } (raw_params; LoopConfig.fused_wrapper=False: the
+        gaussian_renderer/__init__.py:188-196)                                   stand-alone lsx_pose_transform / lsx_gaussian_head)
     rasterizer forward                                                         lsx_rasterize_forward
     depth -> normal * alpha.detach() (gaussian_renderer/__init__.py:233-235)   lsx_depth_normal_forward
     (1 - l) L1 + l (1 - SSIM)                 (gaussian_field.py:238-246)      lsx_image_loss_forward
@@ -70,6 +70,9 @@ class LoopConfig:
     # collective after it.  Measured at C4 on 2 GPUs (profiles/r6e_c4loop_n2*.json): 11.47 vs 11.08 ms per step — five small
     # collectives and NCCL's CTAs competing with the wrapper's backward cost more than the 0.28 ms they hide; off by default.
     overlap_allreduce: bool = False
+    # the render wrapper's per-Gaussian work (pose transform, activations, plane normal, all_map) and its backward inside the
+    # rasterizer's per-Gaussian kernels (lsx_forward_args.raw_params) instead of in separate passes over P
+    fused_wrapper: bool = True
 
 
 @dataclass
@@ -182,16 +185,23 @@ class FieldLoop:
         losses = {}
 
         # -- forward --
-        xyz, rot_in, pose_tape = pv["means3D"], pv["rotations"], None
-        if cfg.optimise_pose:
-            pose_tape = _Tape()
-            xyz, rot_in = _PoseTransform.forward(pose_tape, pv["pose"][view.index], pv["means3D"], pv["rotations"])
-        scales, rotations, opacity, all_map = self._head_forward(xyz, rot_in, view)
         e = self._empty
-        fwd = ops.rasterize_gaussians(self.bg, xyz, e, pv["language_feature"], pv["instance_feature"], opacity, scales,
-                                      rotations, 1.0, e, all_map, view.viewmatrix, view.projmatrix, view.tanfovx,
-                                      view.tanfovy, H, W, pv["sh"].view(P, self.M, 3), cfg.sh_degree, view.campos, False,
-                                      True, False, True)
+        pose_row = pv["pose"][view.index] if cfg.optimise_pose else None
+        xyz, rot_in, pose_tape = pv["means3D"], pv["rotations"], None
+        if cfg.fused_wrapper:
+            fwd = ops.rasterize_gaussians(self.bg, pv["means3D"], e, pv["language_feature"], pv["instance_feature"], pv["opacity"],
+                                          pv["scales"], pv["rotations"], 1.0, e, e, view.viewmatrix, view.projmatrix, view.tanfovx,
+                                          view.tanfovy, H, W, pv["sh"].view(P, self.M, 3), cfg.sh_degree, view.campos, False,
+                                          True, False, True, raw_params=True, pose=pose_row)
+        else:
+            if cfg.optimise_pose:
+                pose_tape = _Tape()
+                xyz, rot_in = _PoseTransform.forward(pose_tape, pose_row, pv["means3D"], pv["rotations"])
+            scales, rotations, opacity, all_map = self._head_forward(xyz, rot_in, view)
+            fwd = ops.rasterize_gaussians(self.bg, xyz, e, pv["language_feature"], pv["instance_feature"], opacity, scales,
+                                          rotations, 1.0, e, all_map, view.viewmatrix, view.projmatrix, view.tanfovx,
+                                          view.tanfovy, H, W, pv["sh"].view(P, self.M, 3), cfg.sh_degree, view.campos, False,
+                                          True, False, True)
         (R, color, lang, inst, radii, observe, amap, depth, geom, binning, img) = fwd
 
         # -- image-space losses: forward + their backward, called directly (no autograd graph) --
@@ -223,6 +233,34 @@ class FieldLoop:
         else:
             g_lang = self._zeros(self.F, H, W)
         g_inst = self._zeros(self.Fi, H, W)
+
+        if cfg.fused_wrapper:
+            # -- rasterizer + wrapper backward in one: EVERY parameter gradient (and the pose row) goes straight into the arena --
+            sink = {k: gv[k] for k in ("means3D", "sh", "opacity", "scales", "rotations", "language_feature", "instance_feature")}
+            bwd = ops.rasterize_gaussians_backward(self.bg, amap, pv["means3D"], radii, e, pv["language_feature"],
+                                                   pv["instance_feature"], e, pv["scales"], pv["rotations"], 1.0, e,
+                                                   view.viewmatrix, view.projmatrix, view.tanfovx, view.tanfovy, g_color, g_lang,
+                                                   g_inst, g_amap, g_depth, pv["sh"].view(P, self.M, 3), cfg.sh_degree, view.campos,
+                                                   geom, R, binning, img, True, False, True, grad_buffers=sink, accumulate=acc,
+                                                   raw_params=True, pose=pose_row,
+                                                   pose_grad=gv["pose"][view.index] if cfg.optimise_pose else None,
+                                                   accumulate_pose=True)
+            g_m2d, g_m2d_abs = bwd[0], bwd[1]
+            if self.debug_tap is not None:
+                self.debug_tap.append({k: v.detach().clone() for k, v in dict(
+                    color=color, lang=lang, amap=amap, depth=depth, g_color=g_color, g_lang=g_lang, g_amap=g_amap, g_depth=g_depth,
+                    g_m2d=g_m2d).items()})
+            if cfg.cls3d and sample_idx is not None:
+                t_c = _Tape()
+                cls_loss, _nbr = _Cls3d.forward(t_c, pv["means3D"], pv["language_feature"], sample_idx, cfg.reg3d_k, cfg.reg3d_lambda)
+                gv["language_feature"].add_(_Cls3d.backward(t_c, self._g_one, None)[1])
+                losses["cls3d"] = cls_loss
+            if last and self.world > 1 and cfg.overlap_allreduce:
+                spans = list(_SPANS_AFTER_RASTER) + list(_SPANS_AFTER_HEAD) + ([("pose",)] if cfg.optimise_pose else [])
+                pending.extend(self.grads.all_reduce_spans(spans, self.group))
+            if stats is not None:
+                add_densification_stats(stats, g_m2d, g_m2d_abs, radii, observe)
+            return losses
 
         # -- rasterizer backward: sh / language / instance gradients go straight into the arena --
         sink = {"sh": gv["sh"], "language_feature": gv["language_feature"], "instance_feature": gv["instance_feature"]}

@@ -117,7 +117,13 @@ def rasterize_gaussians(
     background, means3D, colors, language_feature, language_feature_instance, opacity, scales, rotations,
     scale_modifier, cov3D_precomp, all_map, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width,
     sh, degree, campos, prefiltered, render_geo, debug, include_feature,
+    *, raw_params=False, pose=None,
 ):
+    """Positional signature of the reference's `_C.rasterize_gaussians`.  Keyword-only extension (fused render wrapper,
+    lsx_forward_args.raw_params): with `raw_params=True`, `means3D / opacity / scales / rotations` are the reference's RAW
+    parameters (positions, opacity logits, log-scales, un-normalised quaternions), `all_map` and `cov3D_precomp` must be empty,
+    `pose` is an optional (7,) camera pose [quaternion | translation]; the per-Gaussian kernel applies pose transform,
+    activations, plane normal and all_map itself."""
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -186,6 +192,14 @@ def rasterize_gaussians(
         a.out_all_map, a.out_plane_depth = out_all_map.data_ptr(), out_plane_depth.data_ptr()
         a.geom_alloc, a.binning_alloc, a.image_alloc = geom.fn, binning.fn, image.fn
         a.stream = _stream_handle(device)
+        if raw_params:
+            if (all_map is not None and all_map.numel()) or (cov3D_precomp is not None and cov3D_precomp.numel()):
+                raise RuntimeError("raw_params=True takes neither all_map nor cov3D_precomp")
+            a.raw_params = 1
+            pose = _prep(pose, "pose", device)
+            if pose is not None and pose.numel() not in (0, 7):
+                raise RuntimeError("pose must have 7 elements [quaternion | translation]")
+            a.pose = _ptr(pose)
         hint_key = (device.index, P, H, W, n_blend)
         a.binning_capacity_hint = 0 if debug else _capacity_hint(hint_key)
         rendered = ctypes.c_int32(0)
@@ -216,14 +230,18 @@ def rasterize_gaussians_backward(
     scales, rotations, scale_modifier, cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy,
     dL_dout_color, dL_dout_language_feature, dL_dout_language_feature_instance, dL_dout_all_map, dL_dout_plane_depth,
     sh, degree, campos, geomBuffer, R, binningBuffer, imageBuffer, render_geo, debug, include_feature,
-    *, grad_buffers=None, accumulate=False,
+    *, grad_buffers=None, accumulate=False, raw_params=False, pose=None, pose_grad=None, accumulate_pose=False,
 ):
     """Positional signature of the reference's `_C.rasterize_gaussians_backward`.  Keyword-only extensions for
     multi-view optimisation: `grad_buffers` maps any of {"means3D", "sh", "opacity", "scales", "rotations", "colors",
     "language_feature", "instance_feature", "all_map", "cov3D"} to a caller-owned contiguous fp32 tensor (e.g. a view
     into lsx_b200.multiview.GradArena) that receives that gradient instead of a fresh tensor; with `accumulate=True`
     the gradients of exactly those groups are ADDED to the buffers (the kernel does the read-modify-write, no extra pass);
-    all other outputs are fresh tensors holding this view's gradient."""
+    all other outputs are fresh tensors holding this view's gradient.
+    Fused render wrapper (`raw_params=True`, same `pose` as the forward call): `means3D / scales / rotations` are the RAW
+    parameters and the returned (or sunk) means3D / scales / rotations / opacity gradients are those of the raw parameters;
+    the cov3D and all_map entries of the tuple are not written (empty); `pose_grad` (7,) receives the pose gradient (added to
+    when `accumulate_pose`)."""
     lib = _lib.load()
     if not means3D.is_cuda:
         raise RuntimeError("means3D must be a CUDA tensor (this operator has no CPU path)")
@@ -313,6 +331,16 @@ def rasterize_gaussians_backward(
             a.stream = _stream_handle(device)
             a.accumulate_param_grads = acc_mask
             a.binning_bytes = int(binningBuffer.numel()) if binningBuffer is not None else 0
+            if raw_params:
+                a.raw_params = 1
+                pose = _prep(pose, "pose", device)
+                a.pose = _ptr(pose)
+                a.dL_dcov3D, a.dL_dall_map = None, None
+                if pose_grad is not None:
+                    if pose_grad.numel() != 7 or pose_grad.dtype != _FLOAT or not pose_grad.is_contiguous():
+                        raise RuntimeError("pose_grad must be a contiguous float32 tensor of 7 elements")
+                    a.dL_dpose = pose_grad.data_ptr()
+                    a.accumulate_pose = int(bool(accumulate_pose))
             _lib.check(lib.lsx_rasterize_backward(ctypes.byref(a)), "rasterize_gaussians_backward")
 
     return (g_means2D, g_means2D_abs, g_colors, g_lang, g_inst, g_opacity, g_means3D, g_cov3D, g_sh, g_scales, g_rot,

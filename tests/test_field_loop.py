@@ -62,13 +62,15 @@ def _autograd_gradient(raw, views, poses, cfg, sample_idx, bg):
     return g, m2s
 
 
-@pytest.mark.parametrize("optimise_pose", [True, False])
-def test_hand_chained_backward_equals_autograd_composition(optimise_pose):
+@pytest.mark.parametrize("optimise_pose,fused", [(True, True), (False, True), (True, False), (False, False)])
+def test_hand_chained_backward_equals_autograd_composition(optimise_pose, fused):
+    """fused = the wrapper's per-Gaussian work inside the rasterizer's preprocess kernels (lsx_forward_args.raw_params);
+    not fused = the stand-alone pose / head kernels around the reference-shaped rasterizer call.  Both against autograd."""
     import bench_loop as bl
     from lsx_b200.field_loop import FieldLoop, LoopConfig
     raw, views, poses = _case()
     P = raw["means3D"].shape[0]
-    cfg = LoopConfig(optimise_pose=optimise_pose)
+    cfg = LoopConfig(optimise_pose=optimise_pose, fused_wrapper=fused)
     bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
     si = [bl.sample_indices(v.index, 0, P, cfg.reg3d_samples, DEV) for v in views]
     loop = FieldLoop(raw, bl.LRS, bg, cfg, n_views=len(views), poses=poses)
@@ -96,8 +98,10 @@ def test_hand_chained_backward_equals_autograd_composition(optimise_pose):
         # 1e-4 tensor-scale; a chaining error (missing term, wrong sign, wrong buffer, missing accumulation) is O(1).
         v2 = again.grads.views[name]
         report[name] = dict(rms=(rms(v, r), rms(v2, v)), scale=(hz.rel_err(v, r), hz.rel_err(v2, v)))
-        assert rms(v, r) < max(2e-5, 4.0 * rms(v2, v)), (name, report[name])
-        assert hz.rel_err(v, r) < max(1e-4, 4.0 * hz.rel_err(v2, v)), (name, report[name])
+        # fused: the wrapper's forward runs inside another kernel than in the autograd composition; a different FMA contraction
+        # there moves a position by an ulp, which now and then flips a radius or an alpha >= 1/255 test of some splat
+        assert rms(v, r) < max(5e-5 if fused else 2e-5, 4.0 * rms(v2, v)), (name, report[name])
+        assert hz.rel_err(v, r) < max(3e-4 if fused else 1e-4, 4.0 * hz.rel_err(v2, v)), (name, report[name])
     print("field loop vs autograd composition, (error, run-to-run spread of the hand-chained step):", report)
     # densification statistics: the per-step delta merged into the persistent ones = the reference's per-view updates
     from lsx_b200.multiview import DensifyStats
@@ -218,3 +222,35 @@ def test_mark_visible_matches_the_reference_export():
         theirs = ref.mark_visible(scene.means3D, cam.viewmatrix, cam.projmatrix)
         assert mine.dtype == theirs.dtype == torch.bool and torch.equal(mine, theirs)
         assert 0 < int(mine.sum()) < P or P == 1
+
+
+@pytest.mark.parametrize("optimise_pose", [True, False])
+def test_fused_wrapper_renders_what_the_unfused_chain_renders(optimise_pose):
+    """raw_params mode of the rasterizer against pose_transform -> gaussian_head -> reference-shaped call: the same device
+    functions run in both, so images agree to fp32 rounding (FMA contraction may differ between the two kernels) and the list
+    length by at most a few radius flips."""
+    import bench_loop as bl
+    from lsx_b200 import ops, render_utils as RU
+    raw, views, poses = _case(P=15_000)
+    vw = views[1]
+    P = raw["means3D"].shape[0]
+    e = torch.Tensor([])
+    bg = torch.tensor([0.2, 0.1, 0.3], device=DEV)
+    pose = poses[1].contiguous() if optimise_pose else None
+    sh = raw["sh"].reshape(P, -1, 3).contiguous()
+    common = (vw.viewmatrix, vw.projmatrix, vw.tanfovx, vw.tanfovy, vw.H, vw.W, sh, 3, vw.campos, False, True, False, True)
+    fused = ops.rasterize_gaussians(bg, raw["means3D"], e, raw["language_feature"], raw["instance_feature"], raw["opacity"],
+                                    raw["scales"], raw["rotations"], 1.0, e, e, *common, raw_params=True, pose=pose)
+    xyz, rot = raw["means3D"], raw["rotations"]
+    if optimise_pose:
+        xyz, rot = RU.pose_transform(pose, xyz, rot)
+    scales, rots, opac, all_map = RU.gaussian_head(xyz, raw["scales"], rot, raw["opacity"], vw.viewmatrix, vw.campos)
+    plain = ops.rasterize_gaussians(bg, xyz.contiguous(), e, raw["language_feature"], raw["instance_feature"], opac, scales, rots, 1.0, e,
+                                    all_map, *common)
+    assert abs(fused[0] - plain[0]) <= max(4, int(1e-4 * plain[0])), (fused[0], plain[0])
+    assert int((fused[4] != plain[4]).sum()) <= 4                                   # radii
+    for k, name in ((1, "color"), (2, "language"), (3, "instance"), (6, "all_map"), (7, "plane_depth")):
+        assert hz.rel_err(fused[k], plain[k]) < 1e-4, (name, hz.rel_err(fused[k], plain[k]))
+    with pytest.raises(RuntimeError, match="all_map"):
+        ops.rasterize_gaussians(bg, raw["means3D"], e, raw["language_feature"], raw["instance_feature"], raw["opacity"],
+                                raw["scales"], raw["rotations"], 1.0, e, all_map, *common, raw_params=True)

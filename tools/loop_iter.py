@@ -25,4 +25,10 @@ si = [bl.sample_indices(v, 0, c["P"], 800, dev) for v in range(V)] if cfg.cls3d 
 for _ in range(steps):
     loop.step(views, si)
 torch.cuda.synchronize()
-print("loop_iter done", name, V, steps)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    loop.step(views, si)
+e1.record()
+torch.cuda.synchronize()
+print("loop_iter done", name, V, steps, "ms_per_view", round(e0.elapsed_time(e1) / (steps * V), 4), "lib", os.environ.get("LSX_B200_LIB", "default"))
