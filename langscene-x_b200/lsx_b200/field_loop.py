@@ -342,6 +342,46 @@ class FieldLoop:
             pending.wait()
             return {k: torch.stack(v).sum() for k, v in totals.items()}
 
+    # ---- densification on the replica's arenas (gaussian_field.py:526-535) ------------------------------------------------
+    def _gaussian_groups(self, flat: torch.Tensor) -> GradArena:
+        """An arena object over the per-Gaussian groups of `flat` (same memory; the pose rows at the tail are left out)."""
+        offs = {n: oc for n, oc in self.params.offsets.items() if n != "pose"}
+        views = {n: flat[o:o + c].view(self.params.views[n].shape) for n, (o, c) in offs.items()}
+        return GradArena(flat, views, offs)
+
+    def densify_and_prune(self, max_grad: float, abs_max_grad: float, min_opacity: float, extent: float, max_screen_size=None,
+                          dcfg=None, generator=None):
+        """GaussianModel.densify_and_prune (gaussian_model.py:700-718) on this replica: plan from the PERSISTENT statistics
+        (identical on every rank: only all-reduced deltas were ever merged into them), one gather per arena for parameters and
+        both Adam moments, statistics restarted.  With equally seeded `generator`s every rank samples the same new Gaussians,
+        so the replicas stay bit-identical without any broadcast.  Returns lsx_b200.densify.DensifyResult."""
+        from .densify import DensifyConfig, densify_and_prune
+        with torch.cuda.device(self.device):
+            res = densify_and_prune(self._gaussian_groups(self.params.flat), self._gaussian_groups(self.opt.exp_avg),
+                                    self._gaussian_groups(self.opt.exp_avg_sq), self.stats, dcfg or DensifyConfig(), max_grad,
+                                    abs_max_grad, min_opacity, extent, max_screen_size, generator=generator)
+            P_new = next(iter(res.params.views.values())).shape[0]
+            extra = {"pose": tuple(self.params.views["pose"].shape)} if self.cfg.optimise_pose else None
+            new = [GradArena.allocate(P_new, self.M, self.F, self.Fi, self.device, extra=extra) for _ in range(3)]
+            for dst, src_new, src_old in zip(new, (res.params, res.exp_avg, res.exp_avg_sq),
+                                             (self.params.flat, self.opt.exp_avg, self.opt.exp_avg_sq)):
+                g = src_new.flat.numel() if P_new > 0 else 0
+                dst.flat[:g].copy_(src_new.flat[:g])                       # identical group order and 256-B alignment
+                if self.cfg.optimise_pose:
+                    o_new, c = dst.offsets["pose"]
+                    o_old, _ = self.params.offsets["pose"]
+                    dst.flat[o_new:o_new + c].copy_(src_old[o_old:o_old + c])
+            self.params = new[0]
+            self.grads = GradArena.allocate(P_new, self.M, self.F, self.Fi, self.device, extra=extra)
+            self.opt.rebind(self.params, new[1].flat, new[2].flat)
+            self.stats, self._delta, self.P = res.stats, DensifyStats.allocate(P_new, self.device), P_new
+        return res
+
+    def reset_opacity(self):
+        """GaussianModel.reset_opacity (gaussian_model.py:443-446) in place, Adam moments of the opacity group zeroed."""
+        from .densify import reset_opacity
+        reset_opacity(self.params, self._gaussian_groups(self.opt.exp_avg), self._gaussian_groups(self.opt.exp_avg_sq))
+
     def step(self, views: Sequence[View], sample_idx: Optional[Sequence[torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
         losses = self.gradient(views, sample_idx)
         with torch.cuda.device(self.device):

@@ -254,3 +254,59 @@ def test_fused_wrapper_renders_what_the_unfused_chain_renders(optimise_pose):
     with pytest.raises(RuntimeError, match="all_map"):
         ops.rasterize_gaussians(bg, raw["means3D"], e, raw["language_feature"], raw["instance_feature"], raw["opacity"],
                                 raw["scales"], raw["rotations"], 1.0, e, all_map, *common, raw_params=True)
+
+
+def test_densify_inside_the_loop_keeps_arenas_and_optimiser_consistent():
+    """steps -> densify_and_prune on the replica's arenas (statistics from the loop itself) -> steps: the Gaussian count changes,
+    parameters / moments / pose rows carry over, the statistics restart, training goes on."""
+    import bench_loop as bl
+    from lsx_b200.field_loop import FieldLoop, LoopConfig
+    raw, views, poses = _case(P=12_000, W=160, H=112)
+    P = raw["means3D"].shape[0]
+    cfg = LoopConfig()
+    si = [bl.sample_indices(v.index, 0, P, cfg.reg3d_samples, DEV) for v in views]
+    loops = [FieldLoop(raw, bl.LRS, torch.zeros(3, device=DEV), cfg, n_views=len(views), poses=poses)]
+    for loop in loops:
+        for _ in range(4):
+            loop.step(views, si)
+        pose_before = loop.params.views["pose"].clone()
+        sh_before = loop.params.views["sh"].clone()
+        gen = torch.Generator(device=DEV).manual_seed(1234)
+        # thresholds far below the accumulated screen-space gradients: plenty of clones / splits, some pruning
+        res = loop.densify_and_prune(1e-7, 4e-7, 0.02, 4.0, 20, generator=gen)
+        assert loop.P != P and loop.P == loop.params.views["means3D"].shape[0] == loop.grads.views["means3D"].shape[0]
+        assert res.n_clone + res.n_split > 0
+        assert torch.equal(loop.params.views["pose"], pose_before)
+        assert float(loop.stats.denom.abs().max()) == 0.0 and loop.stats.denom.numel() == loop.P
+        assert loop.opt.exp_avg.numel() == loop.params.flat.numel()
+        kept = res.n_kept_original
+        assert kept > 0 and loop.params.views["sh"].shape[0] == loop.P and sh_before.shape[0] == P
+        si2 = [bl.sample_indices(v.index, 1, loop.P, cfg.reg3d_samples, DEV) for v in views]
+        out = loop.step(views, si2)
+        assert all(bool(torch.isfinite(v)) for v in out.values()) and bool(torch.isfinite(loop.params.flat).all())
+        loop.reset_opacity()
+        assert float(torch.sigmoid(loop.params.views["opacity"]).max()) <= 0.0101
+
+
+def test_densify_is_bit_reproducible_across_replicas_with_equal_state():
+    """Two replicas holding equal bits (what an all-reduced step leaves on every rank) and equally seeded generators build
+    bit-identical arenas: view-sharded ranks stay in step through densification without any broadcast."""
+    import bench_loop as bl
+    from lsx_b200.field_loop import FieldLoop, LoopConfig
+    raw, views, poses = _case(P=9_000, W=160, H=112)
+    cfg = LoopConfig()
+    si = [bl.sample_indices(v.index, 0, raw["means3D"].shape[0], cfg.reg3d_samples, DEV) for v in views]
+    a = FieldLoop(raw, bl.LRS, torch.zeros(3, device=DEV), cfg, n_views=len(views), poses=poses)
+    for _ in range(3):
+        a.step(views, si)
+    b = FieldLoop(raw, bl.LRS, torch.zeros(3, device=DEV), cfg, n_views=len(views), poses=poses)
+    b.params.flat.copy_(a.params.flat)                       # what an all-reduced step leaves on every rank: equal bits
+    b.opt.exp_avg.copy_(a.opt.exp_avg)
+    b.opt.exp_avg_sq.copy_(a.opt.exp_avg_sq)
+    for n in ("grad_accum", "grad_accum_abs", "denom", "max_radii2D"):
+        getattr(b.stats, n).copy_(getattr(a.stats, n))
+    for loop in (a, b):
+        loop.densify_and_prune(1e-7, 4e-7, 0.02, 4.0, 20, generator=torch.Generator(device=DEV).manual_seed(77))
+    assert a.P == b.P and a.P != raw["means3D"].shape[0]
+    assert torch.equal(a.params.flat.view(torch.int32), b.params.flat.view(torch.int32))
+    assert torch.equal(a.opt.exp_avg.view(torch.int32), b.opt.exp_avg.view(torch.int32))
