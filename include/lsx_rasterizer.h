@@ -460,7 +460,9 @@ LSX_API int32_t lsx_binning_capacity(size_t binning_bytes, int32_t W, int32_t H)
  *   [0] S   sum of n_contrib = (pixel, entry) tests per pass of the reference's render loops (forward.cu:335-407)
  *   [1] B   (pixel, entry) pairs actually blended (alpha >= 1/255, power <= 0, at or before the pixel's last contributor)
  *   [2] V   (8x4 block, entry) visits of this library's backward pass      [3] Vb  visits in which some pixel blends
- *   [4] L   total length of the per-block compacted lists                  [5..7] reserved (0) */
+ *   [4] L   total length of the per-block compacted lists
+ *   [5] Hmax, [6] Hsum   what-if counters for 4x4-pixel cells (two per block): sum over blocks of the larger / of both halves'
+ *                        counts of visits in which that half blends                                   [7] reserved (0) */
 LSX_API int lsx_render_stats(int32_t P, int32_t W, int32_t H, int32_t R, int32_t n_blend_channels, const char* geom_buffer,
                      const char* binning_buffer, size_t binning_bytes, const char* image_buffer, uint64_t* stats_out,
                      void* stream);

@@ -9,7 +9,8 @@
 //          deepest contributor of any of its pixels
 //   Vb     visits in which at least one of the 32 pixels blends
 //   L      total length of the per-block compacted lists (what the forward walks at most)
-//   Bmax   sum over visits-with-a-blend of 32 (lane slots issued for blending): B / Bmax = lane utilisation
+//   Hmax   what-if counter for 4x4-pixel cells: sum over blocks of max(visits in which the left half blends, ... the right half)
+//   Hsum   sum over blocks of both halves' blending visits
 //
 // One warp per 8x4 block, the same pixel <-> lane mapping as the render kernels.  Not on the timed path: bench.py and the
 // tests call it once per view for the roofline's flop model.
@@ -39,6 +40,7 @@ __global__ void __launch_bounds__(32) render_stats_kernel(const RenderParams p, 
     const uint32_t* list = p.blk_list + (size_t)warp * p.list_stride + range.x;
 
     unsigned long long B = 0ull, Vb = 0ull;
+    unsigned c0 = 0u, c1 = 0u;  // visits in which the left / right 4x4 half of the block blends (what-if: 4x4-pixel cells)
     for (int e = 0; e < n_eff; ++e) {
         const uint32_t id = __ldg(p.point_list + range.x + __ldg(list + e));
         const float* rec = p.records + (size_t)id * p.rec_stride;
@@ -51,6 +53,8 @@ __global__ void __launch_bounds__(32) render_stats_kernel(const RenderParams p, 
         const unsigned m = __ballot_sync(kFull, blend);
         B += blend ? 1ull : 0ull;
         Vb += (m != 0u && lane == 0u) ? 1ull : 0ull;
+        c0 += (m & 0x0f0f0f0fu) ? 1u : 0u;  // lanes with (lane & 7) < 4
+        c1 += (m & 0xf0f0f0f0u) ? 1u : 0u;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -63,6 +67,10 @@ __global__ void __launch_bounds__(32) render_stats_kernel(const RenderParams p, 
         if (n_eff) atomicAdd(out + 2, (unsigned long long)n_eff);
         if (Vb) atomicAdd(out + 3, Vb);
         if (cnt) atomicAdd(out + 4, (unsigned long long)cnt);
+        if (c0 | c1) {
+            atomicAdd(out + 5, (unsigned long long)(c0 > c1 ? c0 : c1));  // iterations of a warp walking both halves' lists in step
+            atomicAdd(out + 6, (unsigned long long)(c0 + c1));            // (4x4 cell, entry) visits in which the cell blends
+        }
     }
 }
 

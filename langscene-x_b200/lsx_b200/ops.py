@@ -395,4 +395,4 @@ def render_stats(num_rendered, geomBuffer, binningBuffer, imageBuffer, P, image_
                                         _ptr(geomBuffer), _ptr(binningBuffer), int(binningBuffer.numel()), _ptr(imageBuffer),
                                         out.data_ptr(), _stream_handle(device)), "render_stats")
         v = out.cpu().tolist()
-    return {"S": v[0], "B": v[1], "V": v[2], "Vb": v[3], "L": v[4], "R": int(num_rendered)}
+    return {"S": v[0], "B": v[1], "V": v[2], "Vb": v[3], "L": v[4], "R": int(num_rendered), "Hmax": v[5], "Hsum": v[6]}

@@ -35,7 +35,7 @@ for name in (sys.argv[1:] or ["C1", "C2", "C3", "C4", "C5"]):
     row = {"config": name, "P": c["P"], "W": c["W"], "H": c["H"], "F": c["F"], "R": int(fwd["num_rendered"]),
            "P_vis": int((fwd["radii"] > 0).sum())}
     st = ops.render_stats(fwd["num_rendered"], fwd["geom"], fwd["binning"], fwd["img"], c["P"], c["H"], c["W"], 3 + c["F"] + 3 + 5)
-    row.update({k: st[k] for k in ("S", "B", "V", "Vb", "L")})
+    row.update({k: st[k] for k in ("S", "B", "V", "Vb", "L", "Hmax", "Hsum")})
     row["lane_utilisation_in_blending_visits"] = round(st["B"] / max(1, 32 * st["Vb"]), 3)
     del fwd
     n = 20 if c["P"] <= 1_000_000 else 5
