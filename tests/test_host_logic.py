@@ -216,3 +216,21 @@ def test_binning_capacity_is_recovered_from_the_buffer_size():
             assert lib.lsx_scratch_layout_query(10, W, H, cap, 27, ctypes.byref(lay)) == 0
             assert lib.lsx_binning_capacity(lay.binning_bytes, W, H) == cap, (W, H, cap)
             assert lib.lsx_binning_capacity(lay.binning_bytes + 8, W, H) == -1        # not a size any capacity produces
+
+
+def test_reference_arm_imports_do_not_load_the_product_library():
+    """`bench.py --impl reference` must not map liblsx_b200.so (the driver records which in-tree libraries a process loaded):
+    everything that arm imports before it starts timing — bench, harness, the pure-torch arena / scene modules, the loop
+    bench with its reference-style arm — is imported in a fresh interpreter and /proc/self/maps is inspected."""
+    code = (
+        "import sys\n"
+        f"sys.path[:0] = [{os.path.join(hz.REPO, 'langscene-x_b200')!r}, {hz.REPO!r}, {os.path.join(hz.REPO, 'tests')!r}]\n"
+        "import torch, harness, bench, bench_loop\n"
+        "from lsx_b200.multiview import GradArena\n"
+        "from lsx_b200.synthetic import CONFIGS\n"
+        "from lsx_b200.field_loop import LoopConfig, View\n"
+        "GradArena.allocate(10, 16, 3, 3, 'cpu')\n"
+        "print('LOADED' if 'liblsx_b200' in open('/proc/self/maps').read() else 'CLEAN')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().endswith("CLEAN"), out.stdout
