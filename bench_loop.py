@@ -472,6 +472,8 @@ def loop_step_streamed(loop, si, feeder):
             loop.grads.views["pose"].zero_()
         n = feeder.n
         totals = {}
+        from lsx_b200.loss import knn_tree
+        loop._tree = knn_tree(loop.params.views["means3D"]) if (loop.cfg.cls3d and loop.cfg.cls3d_tree and si is not None) else None
         for i in range(n):
             res = loop._view(feeder.next_view(), i == 0, i == n - 1, si[i] if si is not None else None, pending, delta)
             feeder.release()

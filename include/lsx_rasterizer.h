@@ -396,6 +396,15 @@ LSX_API int64_t lsx_cls3d_scratch_bytes(int32_t N, int32_t C, int32_t S, int32_t
 LSX_API int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
                               const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax,
                               void* scratch, void* stream);
+/* The same with the neighbour search through a prebuilt search structure over `points` (Morton order + 3-level box hierarchy,
+ * the one lsx_knn_mean_dist2 builds for itself): build it once with lsx_knn_tree_build into a device buffer of
+ * lsx_knn_tree_bytes(N) bytes and reuse it for every call made before the points change — e.g. once per optimisation step for
+ * all views of the step.  Exact: the same neighbours, in the same order, as the brute-force search of lsx_cls3d_forward. */
+LSX_API int64_t lsx_knn_tree_bytes(int32_t N);
+LSX_API int lsx_knn_tree_build(int32_t N, const float* points, void* tree, void* stream);
+LSX_API int lsx_cls3d_forward_tree(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
+                           const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax,
+                           void* scratch, const void* tree, void* stream);
 LSX_API int lsx_cls3d_backward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* preds,
                                const int32_t* sample_idx, const int32_t* nbr_idx, const float* minmax, const float* upstream,
                                float* dL_dpreds, void* scratch, void* stream);

@@ -435,13 +435,21 @@ __global__ void __launch_bounds__(256) cls3d_finalize_grad_kernel(const long lon
 template <int K>
 int launch_forward_k(const int N, const int C, const int S, const Cls3dLayout& L, const float* points, const float* preds,
                      const int* sample_idx, char* scratch, int* nbr_idx, float* minmax, const int mm_blocks,
-                     cudaStream_t stream) {
+                     const void* tree, cudaStream_t stream) {
     float* cand_d = reinterpret_cast<float*>(scratch + L.cand_d_off);
     int* cand_i = reinterpret_cast<int*>(scratch + L.cand_i_off);
     const int groups = ceil_div(S, kQueriesPerBlock);
-    cls3d_knn_kernel<K><<<dim3(groups, L.slices), 256, 0, stream>>>(N, S, L.slices, points, sample_idx, cand_d, cand_i);
-    LSX_KERNEL_OK(stream, false);
-    cls3d_merge_kernel<K><<<groups, 256, 0, stream>>>(N, C, S, L.slices, preds, sample_idx, cand_d, cand_i,
+    int slices = L.slices;
+    if (tree != nullptr) {
+        // neighbour search through a prebuilt Morton / box hierarchy of the points (knn.cu): one candidate list per sample
+        slices = 1;
+        const int rc = knn_tree_query(K, N, tree, S, points, sample_idx, cand_d, cand_i, stream);
+        if (rc) return rc;
+    } else {
+        cls3d_knn_kernel<K><<<dim3(groups, L.slices), 256, 0, stream>>>(N, S, L.slices, points, sample_idx, cand_d, cand_i);
+        LSX_KERNEL_OK(stream, false);
+    }
+    cls3d_merge_kernel<K><<<groups, 256, 0, stream>>>(N, C, S, slices, preds, sample_idx, cand_d, cand_i,
                                                       reinterpret_cast<const float*>(scratch + L.mm_off), mm_blocks, nbr_idx,
                                                       minmax, reinterpret_cast<float*>(scratch + L.qsum_off));
     LSX_KERNEL_OK(stream, false);
@@ -465,9 +473,19 @@ extern "C" int64_t lsx_cls3d_scratch_bytes(int32_t N, int32_t C, int32_t S, int3
     return (int64_t)make_layout(N, S, k).total;
 }
 
-extern "C" int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
-                                 const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax,
-                                 void* scratch_, void* stream_) {
+extern "C" int64_t lsx_knn_tree_bytes(int32_t N) { return N > 0 ? (int64_t)knn_temp_bytes(N) : 0; }
+
+extern "C" int lsx_knn_tree_build(int32_t N, const float* points, void* tree, void* stream) {
+    if (N <= 0 || !points || !tree) {
+        set_error("lsx_knn_tree_build: bad arguments");
+        return -1;
+    }
+    return knn_tree_build(N, points, tree, static_cast<cudaStream_t>(stream));
+}
+
+static int cls3d_forward_impl(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points, const float* preds,
+                              const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax, void* scratch_,
+                              const void* tree, void* stream_) {
     if (bad_sizes(N, C, S, k)) {
         set_error("lsx_cls3d_forward: need N, C, S > 0 and 1 <= k <= min(N, %d) (got N=%d C=%d S=%d k=%d)", kMaxK, N, C, S, k);
         return -1;
@@ -486,7 +504,7 @@ extern "C" int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, flo
     int rc = 0;
     switch (k) {
 #define LSX_CLS3D_CASE(KK) \
-    case KK: rc = launch_forward_k<KK>(N, C, S, L, points, preds, sample_idx, scratch, nbr_idx, minmax, mm_blocks, stream); break;
+    case KK: rc = launch_forward_k<KK>(N, C, S, L, points, preds, sample_idx, scratch, nbr_idx, minmax, mm_blocks, tree, stream); break;
         LSX_CLS3D_CASE(1)
         LSX_CLS3D_CASE(2)
         LSX_CLS3D_CASE(3)
@@ -502,6 +520,22 @@ extern "C" int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, flo
     cls3d_finish_kernel<<<1, 256, 0, stream>>>(S, reinterpret_cast<const float*>(scratch + L.qsum_off), scale, loss);
     LSX_KERNEL_OK(stream, false);
     return 0;
+}
+
+extern "C" int lsx_cls3d_forward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
+                                 const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx, float* minmax,
+                                 void* scratch_, void* stream_) {
+    return cls3d_forward_impl(N, C, S, k, lambda_val, points, preds, sample_idx, loss, nbr_idx, minmax, scratch_, nullptr, stream_);
+}
+
+extern "C" int lsx_cls3d_forward_tree(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* points,
+                                      const float* preds, const int32_t* sample_idx, float* loss, int32_t* nbr_idx,
+                                      float* minmax, void* scratch_, const void* tree, void* stream_) {
+    if (!tree) {
+        set_error("lsx_cls3d_forward_tree: null tree");
+        return -1;
+    }
+    return cls3d_forward_impl(N, C, S, k, lambda_val, points, preds, sample_idx, loss, nbr_idx, minmax, scratch_, tree, stream_);
 }
 
 extern "C" int lsx_cls3d_backward(int32_t N, int32_t C, int32_t S, int32_t k, float lambda_val, const float* preds,

@@ -19,6 +19,7 @@
 //   The result is the exact 3-NN set, evaluated with the reference's distance expression, so the
 //   output is bit-identical; no host synchronisation (the reference has two).
 #include <cfloat>
+#include <climits>
 
 #include "kernels.cuh"
 
@@ -250,6 +251,139 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_query_kernel(int P, cons
     if (valid) out[__float_as_uint(q.w)] = (best[0] + best[1] + best[2]) / 3.0f;
 }
 
+// ---- K nearest points of arbitrary dataset points (loss_cls_3d's neighbour search) -------------------------------------
+// One warp per query.  The K best (distance, original index) pairs, ordered lexicographically (ties towards the lower index,
+// like the brute-force scan of cls3d.cu), are kept REPLICATED in every lane; a leaf is scanned with one point per lane and the
+// lanes that beat the current K-th are inserted one by one (few after the seed leaf).  Children are pruned lane-parallel by
+// their point-to-box distance against the K-th distance (kept when equal: an equally distant point may win the tie), with the
+// same slack as the 3-NN kernel; the bound is seeded by a greedy descent to the nearest leaf.  Distances use the expression of
+// cls3d.cu's brute-force kernel, so both routes return the same bits.
+__device__ __forceinline__ float point_box_dist2(const float qx, const float qy, const float qz, const Box& b) {
+    const float gx = fmaxf(0.f, fmaxf(b.lo.x - qx, qx - b.hi.x));
+    const float gy = fmaxf(0.f, fmaxf(b.lo.y - qy, qy - b.hi.y));
+    const float gz = fmaxf(0.f, fmaxf(b.lo.z - qz, qz - b.hi.z));
+    return gx * gx + gy * gy + gz * gz;
+}
+
+__device__ __forceinline__ bool pair_less(const float d0, const int i0, const float d1, const int i1) {
+    return d0 < d1 || (d0 == d1 && i0 < i1);
+}
+
+template <int K>
+__global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P, const float4* __restrict__ spts,
+                                                                          const Box* __restrict__ l1, int n1,
+                                                                          const Box* __restrict__ l2, int n2,
+                                                                          const Box* __restrict__ l3, int n3, int S,
+                                                                          const float* __restrict__ points,
+                                                                          const int* __restrict__ sample_idx,
+                                                                          float* __restrict__ cand_d, int* __restrict__ cand_i) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kQueryWarps + warp;
+    if (s >= S) return;
+    const int si = sample_idx[s];
+    const float qx = points[3 * (size_t)si], qy = points[3 * (size_t)si + 1], qz = points[3 * (size_t)si + 2];
+    float bd[K];
+    int bi[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        bd[j] = FLT_MAX;
+        bi[j] = INT_MAX;
+    }
+    auto scan_leaf = [&](const int leaf) {
+        const int i = leaf * kFan + lane;
+        float d = FLT_MAX;
+        int id = INT_MAX;
+        if (i < P) {
+            const float4 c = spts[i];
+            const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
+            d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            id = (int)__float_as_uint(c.w);
+        }
+        unsigned m = __ballot_sync(kFull, pair_less(d, id, bd[K - 1], bi[K - 1]));
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const float dl = __shfl_sync(kFull, d, l);
+            const int il = __shfl_sync(kFull, id, l);
+            if (!pair_less(dl, il, bd[K - 1], bi[K - 1])) continue;  // the K-th may have improved since the ballot
+#pragma unroll
+            for (int j = K - 1; j > 0; --j) {
+                const bool shift = pair_less(dl, il, bd[j - 1], bi[j - 1]);
+                const bool here = !shift && pair_less(dl, il, bd[j], bi[j]);
+                if (shift) {
+                    bd[j] = bd[j - 1];
+                    bi[j] = bi[j - 1];
+                } else if (here) {
+                    bd[j] = dl;
+                    bi[j] = il;
+                }
+            }
+            if (pair_less(dl, il, bd[0], bi[0])) {
+                bd[0] = dl;
+                bi[0] = il;
+            }
+        }
+    };
+    // index of the child (of `count` boxes starting at `first`) nearest to the query: lane-parallel, lowest index on ties
+    auto nearest_child = [&](const Box* __restrict__ boxes, const int first, const int count) -> int {
+        float best = FLT_MAX;
+        int arg = first;
+        for (int c0 = 0; c0 < count; c0 += 32) {
+            const int i = c0 + lane;
+            const float d = i < count ? point_box_dist2(qx, qy, qz, boxes[first + i]) : FLT_MAX;
+            if (d < best) {
+                best = d;
+                arg = first + i;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(kFull, best, o);
+            const int oa = __shfl_xor_sync(kFull, arg, o);
+            if (od < best || (od == best && oa < arg)) {
+                best = od;
+                arg = oa;
+            }
+        }
+        return arg;
+    };
+    const int s3 = nearest_child(l3, 0, n3);
+    const int s2 = nearest_child(l2, s3 * kFan, min(kFan, n2 - s3 * kFan));
+    const int seed = nearest_child(l1, s2 * kFan, min(kFan, n1 - s2 * kFan));
+    scan_leaf(seed);
+
+    const float kSlack = 1.0f - 1e-5f;
+    for (int c3 = 0; c3 < n3; c3 += 32) {
+        const int i3 = c3 + lane;
+        unsigned m3 = __ballot_sync(kFull, i3 < n3 && !(point_box_dist2(qx, qy, qz, l3[i3 < n3 ? i3 : 0]) * kSlack > bd[K - 1]));
+        while (m3) {
+            const int b3 = c3 + __ffs(m3) - 1;
+            m3 &= m3 - 1;
+            const int i2 = b3 * kFan + lane;
+            unsigned m2 = __ballot_sync(kFull, i2 < n2 && !(point_box_dist2(qx, qy, qz, l2[i2 < n2 ? i2 : 0]) * kSlack > bd[K - 1]));
+            while (m2) {
+                const int b2 = b3 * kFan + __ffs(m2) - 1;
+                m2 &= m2 - 1;
+                const int i1 = b2 * kFan + lane;
+                unsigned m1 = __ballot_sync(kFull, i1 < n1 && i1 != seed &&
+                                                       !(point_box_dist2(qx, qy, qz, l1[i1 < n1 ? i1 : 0]) * kSlack > bd[K - 1]));
+                while (m1) {
+                    const int b1 = b2 * kFan + __ffs(m1) - 1;
+                    m1 &= m1 - 1;
+                    if (point_box_dist2(qx, qy, qz, l1[b1]) * kSlack > bd[K - 1]) continue;  // the bound tightened meanwhile
+                    scan_leaf(b1);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (lane == j) {
+            cand_d[(size_t)s * K + j] = bd[j];
+            cand_i[(size_t)s * K + j] = bi[j];
+        }
+}
+
 struct KnnScratch {
     float* bounds_part;
     float* bounds;
@@ -294,7 +428,8 @@ KnnScratch carve_knn(char* base, int P) {
 
 size_t knn_temp_bytes(int P) { return carve_knn(nullptr, P > 0 ? P : 1).bytes; }
 
-int knn_mean_dist2(int P, const float* points, float* out, void* temp, cudaStream_t stream) {
+// Morton order + float4 stream + 3-level box hierarchy of `points` into `temp` (knn_temp_bytes(P) bytes)
+int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream) {
     if (P <= 0) return 0;
     KnnScratch s = carve_knn(static_cast<char*>(temp), P);
     bounds_partial_kernel<<<s.nb_bounds, 256, 0, stream>>>(P, points, s.bounds_part);
@@ -314,8 +449,46 @@ int knn_mean_dist2(int P, const float* points, float* out, void* temp, cudaStrea
     LSX_KERNEL_OK(stream, false);
     build_boxes_kernel<<<ceil_div(s.n3 * 32, 256), 256, 0, stream>>>(s.n2, nullptr, s.l2, s.l3, s.n3);
     LSX_KERNEL_OK(stream, false);
+    return 0;
+}
+
+int knn_mean_dist2(int P, const float* points, float* out, void* temp, cudaStream_t stream) {
+    if (P <= 0) return 0;
+    const int rc = knn_tree_build(P, points, temp, stream);
+    if (rc) return rc;
+    KnnScratch s = carve_knn(static_cast<char*>(temp), P);
     knn_query_kernel<<<ceil_div(s.n1, kQueryWarps), kQueryWarps * 32, 0, stream>>>(P, s.spts, s.l1, s.n1, s.l2, s.n2, s.l3,
                                                                                    s.n3, out);
+    LSX_KERNEL_OK(stream, false);
+    return 0;
+}
+
+// exact K nearest points (the query itself included) of S dataset points, from a tree built by knn_tree_build over the same
+// `points`: cand_d / cand_i [S][K] sorted by (distance, index) — the layout cls3d.cu's merge kernel takes for one slice
+int knn_tree_query(int K, int P, const void* tree, int S, const float* points, const int* sample_idx, float* cand_d, int* cand_i,
+                   cudaStream_t stream) {
+    if (P <= 0 || S <= 0) return 0;
+    KnnScratch s = carve_knn(const_cast<char*>(static_cast<const char*>(tree)), P);
+    const int blocks = ceil_div(S, kQueryWarps);
+    switch (K) {
+#define LSX_KNN_CASE(KK)                                                                                                       \
+    case KK:                                                                                                                   \
+        knn_tree_query_kernel<KK><<<blocks, kQueryWarps * 32, 0, stream>>>(P, s.spts, s.l1, s.n1, s.l2, s.n2, s.l3, s.n3, S,   \
+                                                                           points, sample_idx, cand_d, cand_i);                \
+        break;
+        LSX_KNN_CASE(1)
+        LSX_KNN_CASE(2)
+        LSX_KNN_CASE(3)
+        LSX_KNN_CASE(4)
+        LSX_KNN_CASE(5)
+        LSX_KNN_CASE(6)
+        LSX_KNN_CASE(7)
+        LSX_KNN_CASE(8)
+#undef LSX_KNN_CASE
+        default:
+            set_error("knn_tree_query: k = %d outside 1..8", K);
+            return -1;
+    }
     LSX_KERNEL_OK(stream, false);
     return 0;
 }

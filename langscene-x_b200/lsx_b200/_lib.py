@@ -140,6 +140,9 @@ EXPORTS = {
     "lsx_cls3d_scratch_bytes": (ctypes.c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "lsx_cls3d_forward": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_float] + [c_void_p] * 8),
     "lsx_cls3d_backward": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_float] + [c_void_p] * 8),
+    "lsx_cls3d_forward_tree": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_float] + [c_void_p] * 9),
+    "lsx_knn_tree_bytes": (ctypes.c_int64, [c_int32]),
+    "lsx_knn_tree_build": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p]),
     "lsx_rows_pack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_rows_unpack": (c_int32, [ctypes.c_int64, c_int32] + [c_void_p] * 5),
     "lsx_scratch_layout_query": (c_int32, [c_int32, c_int32, c_int32, c_int32, c_int32, POINTER(ScratchLayout)]),

@@ -35,7 +35,7 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from .densify import add_densification_stats
-from .loss import _Cls3d, _ImageLoss, _MaskedL1
+from .loss import _Cls3d, _ImageLoss, _MaskedL1, knn_tree
 from .multiview import DensifyStats, GradArena, PendingReduce
 from .optim import ArenaAdam
 from .render_utils import _DepthToNormal, _PoseTransform
@@ -64,6 +64,7 @@ class LoopConfig:
     reg3d_k: int = 5                     # :119
     reg3d_lambda: float = 4.0            # :120
     reg3d_samples: int = 800
+    cls3d_tree: bool = True              # neighbour search through one Morton / box hierarchy per step instead of a scan per view
     optimise_pose: bool = True           # optim_pose (:67)
     densify_stats: bool = True
     # per-group asynchronous all-reduces issued while the last view's backward is still running, instead of ONE blocking
@@ -151,6 +152,7 @@ class FieldLoop:
         self._empty = torch.Tensor([])
         self._zero_img: Dict[tuple, torch.Tensor] = {}
         self.debug_tap = None
+        self._tree = None
         self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
 
@@ -252,7 +254,8 @@ class FieldLoop:
                     g_m2d=g_m2d).items()})
             if cfg.cls3d and sample_idx is not None:
                 t_c = _Tape()
-                cls_loss, _nbr = _Cls3d.forward(t_c, pv["means3D"], pv["language_feature"], sample_idx, cfg.reg3d_k, cfg.reg3d_lambda)
+                cls_loss, _nbr = _Cls3d.forward(t_c, pv["means3D"], pv["language_feature"], sample_idx, cfg.reg3d_k, cfg.reg3d_lambda,
+                                                self._tree)
                 gv["language_feature"].add_(_Cls3d.backward(t_c, self._g_one, None)[1])
                 losses["cls3d"] = cls_loss
             if last and self.world > 1 and cfg.overlap_allreduce:
@@ -278,7 +281,8 @@ class FieldLoop:
         # -- 3-D neighbourhood regulariser on the language feature parameter (adds into the arena) --
         if cfg.cls3d and sample_idx is not None:
             t_c = _Tape()
-            cls_loss, _nbr = _Cls3d.forward(t_c, pv["means3D"], pv["language_feature"], sample_idx, cfg.reg3d_k, cfg.reg3d_lambda)
+            cls_loss, _nbr = _Cls3d.forward(t_c, pv["means3D"], pv["language_feature"], sample_idx, cfg.reg3d_k, cfg.reg3d_lambda,
+                                                self._tree)
             g_feat = _Cls3d.backward(t_c, self._g_one, None)[1]
             gv["language_feature"].add_(g_feat)
             losses["cls3d"] = cls_loss
@@ -328,6 +332,9 @@ class FieldLoop:
             if self.cfg.optimise_pose:
                 self.grads.views["pose"].zero_()
             totals: Dict[str, List[torch.Tensor]] = {}
+            # loss_cls_3d searches neighbours among the positions, which do not change inside a step: one search structure
+            # for all of the step's views (a full scan of the points per view was the largest kernel of a C4-sized iteration)
+            self._tree = knn_tree(self.params.views["means3D"]) if (self.cfg.cls3d and self.cfg.cls3d_tree and sample_idx is not None) else None
             for i, vw in enumerate(views):
                 si = sample_idx[i] if sample_idx is not None else None
                 for k, v in self._view(vw, i == 0, i == len(views) - 1, si, pending, delta).items():

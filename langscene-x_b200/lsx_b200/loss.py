@@ -131,7 +131,7 @@ class _Cls3d(torch.autograd.Function):
     """lambda * mean |q[s] (log(q[s] + eps) - log(q[nbr] + eps))| for given sample rows; gradient to `predictions` only."""
 
     @staticmethod
-    def forward(ctx, features, predictions, sample_idx, k, lambda_val):
+    def forward(ctx, features, predictions, sample_idx, k, lambda_val, tree=None):
         N, C = predictions.shape
         S = int(sample_idx.numel())
         dev = predictions.device
@@ -145,9 +145,14 @@ class _Cls3d(torch.autograd.Function):
         nbr = torch.empty((S, k), dtype=torch.int32, device=dev)
         minmax = torch.empty(2, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(lib.lsx_cls3d_forward(N, C, S, k, float(lambda_val), pts.data_ptr(), pred.data_ptr(), sample_idx.data_ptr(),
-                                             loss.data_ptr(), nbr.data_ptr(), minmax.data_ptr(), scratch.data_ptr(),
-                                             _stream(dev)), "loss_cls_3d")
+            if tree is not None:
+                _lib.check(lib.lsx_cls3d_forward_tree(N, C, S, k, float(lambda_val), pts.data_ptr(), pred.data_ptr(),
+                                                      sample_idx.data_ptr(), loss.data_ptr(), nbr.data_ptr(), minmax.data_ptr(),
+                                                      scratch.data_ptr(), tree.data_ptr(), _stream(dev)), "loss_cls_3d")
+            else:
+                _lib.check(lib.lsx_cls3d_forward(N, C, S, k, float(lambda_val), pts.data_ptr(), pred.data_ptr(),
+                                                 sample_idx.data_ptr(), loss.data_ptr(), nbr.data_ptr(), minmax.data_ptr(),
+                                                 scratch.data_ptr(), _stream(dev)), "loss_cls_3d")
         ctx.save_for_backward(pred, sample_idx, nbr, minmax)
         ctx.k, ctx.lambda_val = k, float(lambda_val)
         ctx.mark_non_differentiable(nbr)
@@ -166,11 +171,35 @@ class _Cls3d(torch.autograd.Function):
             _lib.check(lib.lsx_cls3d_backward(N, C, S, ctx.k, ctx.lambda_val, pred.data_ptr(), sample_idx.data_ptr(),
                                               nbr.data_ptr(), minmax.data_ptr(), up.data_ptr(), out.data_ptr(),
                                               scratch.data_ptr(), _stream(dev)), "loss_cls_3d backward")
-        return None, out, None, None, None
+        return None, out, None, None, None, None
+
+
+class KnnTree:
+    """Opaque search structure of a point set (see `knn_tree`): the device bytes plus the point count they were built for."""
+
+    def __init__(self, data: torch.Tensor, n_points: int):
+        self.data, self.n_points = data, int(n_points)
+
+    def data_ptr(self):
+        return self.data.data_ptr()
+
+
+def knn_tree(points) -> KnnTree:
+    """The search structure (Morton order + box hierarchy) of an (N, 3) float32 CUDA point set for `loss_cls_3d(..., tree=)`.
+    Valid while `points` keeps its values: build it once per optimisation step and share it between the step's views."""
+    if not points.is_cuda or points.dim() != 2 or points.shape[1] != 3 or points.dtype != torch.float32:
+        raise RuntimeError("knn_tree: points must be a float32 (N, 3) CUDA tensor (this operator has no CPU path)")
+    pts = points.detach().contiguous()
+    lib = _lib.load()
+    N = int(pts.shape[0])
+    tree = torch.empty(int(lib.lsx_knn_tree_bytes(N)), dtype=torch.uint8, device=pts.device)
+    with torch.cuda.device(pts.device):
+        _lib.check(lib.lsx_knn_tree_build(N, pts.data_ptr(), tree.data_ptr(), _stream(pts.device)), "knn_tree_build")
+    return KnnTree(tree, N)
 
 
 def loss_cls_3d(features, predictions, k=5, lambda_val=2.0, max_points=200000, sample_size=800, *, sample_indices=None,
-                return_neighbors=False):
+                return_neighbors=False, tree=None):
     """Drop-in for loss_cls_3d of field_construction/utils/loss_utils.py:158-186 (the 3-D neighbourhood regulariser of the
     language / instance features; called with features = xyz.detach(), predictions = the (N, C) feature parameter at
     field_construction/gaussian_field.py:461-465,482-485): same positional signature, same random draws — the optional
@@ -178,7 +207,9 @@ def loss_cls_3d(features, predictions, k=5, lambda_val=2.0, max_points=200000, s
     generator, in the reference's order, so equal seeds select equal rows — but no (samples x N) distance matrix, no topk over
     it and no host read of min / max: the k nearest neighbours are found by a tiled exact scan and the loss, its gradient
     (including the part through the min / max normalisation) and the neighbour indices stay on the device.
-    `sample_indices` (1-D integer tensor) overrides the second draw; 1 <= k <= 8.  Gradient flows to `predictions` only."""
+    `sample_indices` (1-D integer tensor) overrides the second draw; 1 <= k <= 8.  Gradient flows to `predictions` only.
+    `tree` (from `knn_tree(features)`) replaces the scan of all points by a search through a prebuilt hierarchy: same
+    neighbours, same order; reuse it for every call made while the positions are unchanged."""
     if not (features.is_cuda and predictions.is_cuda):
         raise RuntimeError("loss_cls_3d: tensors must be CUDA tensors (this operator has no CPU path)")
     if features.dim() != 2 or features.shape[1] != 3 or features.dtype != torch.float32:
@@ -195,5 +226,7 @@ def loss_cls_3d(features, predictions, k=5, lambda_val=2.0, max_points=200000, s
     if sample_indices is None:                                          # loss_utils.py:172
         sample_indices = torch.randperm(n)[:sample_size]
     idx = sample_indices.to(device=features.device, dtype=torch.int32).contiguous()
-    loss, nbr = _Cls3d.apply(features, predictions, idx, int(k), float(lambda_val))
+    if tree is not None and int(features.size(0)) != tree.n_points:
+        raise RuntimeError("loss_cls_3d: `tree` was built for another point count (it cannot be combined with down-sampling)")
+    loss, nbr = _Cls3d.apply(features, predictions, idx, int(k), float(lambda_val), tree)
     return (loss, nbr) if return_neighbors else loss

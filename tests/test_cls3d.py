@@ -119,3 +119,31 @@ def test_cuda_errors():
         loss_cls_3d(xyz.cuda()[:4], pred.cuda()[:4], k=5)                   # k > N (torch.topk raises in the reference)
     with pytest.raises(RuntimeError):
         loss_cls_3d(xyz.cuda(), pred.cuda()[:10])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,C,k,S,dup", [(500_000, 3, 5, 800, False), (70_000, 16, 8, 300, False), (1500, 3, 5, 64, True),
+                                         (20, 2, 3, 20, False), (33, 1, 1, 7, True)])
+def test_tree_search_returns_the_brute_force_neighbours(N, C, k, S, dup):
+    """loss_cls_3d(..., tree=knn_tree(xyz)): the neighbour search through the Morton / box hierarchy must return exactly what the
+    scan of all points returns — same indices in the same order (ties towards the lower index: `dup` plants coincident points),
+    hence the same loss and gradient bits — at sizes with one, two and three populated hierarchy levels."""
+    from lsx_b200.loss import knn_tree, loss_cls_3d
+    g = torch.Generator().manual_seed(N + k)
+    xyz = (torch.rand(N, 3, generator=g) * 6 - 3)
+    if dup:
+        xyz[N // 2:] = xyz[:N - N // 2].clone()                      # every point of the second half coincides with one of the first
+    xyz = xyz.cuda()
+    pred = torch.randn(N, C, generator=g).cuda()
+    samples = torch.randint(0, N, (S,), generator=g)
+    tree = knn_tree(xyz)
+    out = {}
+    for name, t in (("scan", None), ("tree", tree)):
+        p = pred.clone().requires_grad_(True)
+        loss, nbr = loss_cls_3d(xyz, p, k, 2.0, 10_000_000, S, sample_indices=samples, return_neighbors=True, tree=t)
+        loss.backward()
+        out[name] = (loss.detach(), nbr, p.grad)
+    assert torch.equal(out["scan"][1], out["tree"][1])
+    assert torch.equal(out["scan"][0], out["tree"][0]) and torch.equal(out["scan"][2], out["tree"][2])
+    with pytest.raises(RuntimeError, match="another point count"):
+        loss_cls_3d(xyz[:-1].contiguous(), pred[:-1].contiguous(), k, 2.0, 10_000_000, S, sample_indices=samples % (N - 1), tree=tree)

@@ -51,11 +51,19 @@ for N in (100_000, 500_000, 2_000_000):
         pred.grad = None
         torch_formulation(xyz, pred, 5, 2.0, samples)[0].backward()
 
+    from lsx_b200.loss import knn_tree
+    tree = knn_tree(xyz)
+
+    def fused_tree():
+        pred.grad = None
+        loss_cls_3d(xyz, pred, 5, 2.0, 2_000_000, 800, sample_indices=samples, tree=tree).backward()
+
+    t_build, t_tree = timeit(lambda: knn_tree(xyz)), timeit(fused_tree)
     tf, tt = timeit(fused), timeit(ref)
     lf, nf = loss_cls_3d(xyz, pred, 5, 2.0, 2_000_000, 800, sample_indices=samples, return_neighbors=True)
     lt, nt = torch_formulation(xyz, pred, 5, 2.0, samples)
     same = float((nf.long().sort(dim=1).values == nt.sort(dim=1).values).float().mean())
     print(json.dumps({"op": "loss_cls_3d fwd+bwd", "N": N, "samples": 800, "k": 5, "fused_ms": round(tf, 4),
-                      "torch_ops_ms": round(tt, 4), "speedup": round(tt / tf, 2), "loss_fused": float(lf), "loss_torch_ops": float(lt),
+                      "torch_ops_ms": round(tt, 4), "fused_with_prebuilt_tree_ms": round(t_tree, 4), "tree_build_ms": round(t_build, 4), "speedup": round(tt / tf, 2), "loss_fused": float(lf), "loss_torch_ops": float(lt),
                       "neighbour_entries_equal": round(same, 6),
                       "distance_evals_per_s": round(800 * N / tf * 1e3 / 1e12, 3), "unit": "T evals/s"}), flush=True)
