@@ -252,12 +252,12 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_query_kernel(int P, cons
 }
 
 // ---- K nearest points of arbitrary dataset points (loss_cls_3d's neighbour search) -------------------------------------
-// One warp per query.  The K best (distance, original index) pairs, ordered lexicographically (ties towards the lower index,
-// like the brute-force scan of cls3d.cu), are kept REPLICATED in every lane; a leaf is scanned with one point per lane and the
-// lanes that beat the current K-th are inserted one by one (few after the seed leaf).  Children are pruned lane-parallel by
-// their point-to-box distance against the K-th distance (kept when equal: an equally distant point may win the tie), with the
-// same slack as the 3-NN kernel; the bound is seeded by a greedy descent to the nearest leaf.  Distances use the expression of
-// cls3d.cu's brute-force kernel, so both routes return the same bits.
+// One CTA per query, its warps sharing the level-2 nodes.  Each warp keeps its K best (distance, original index) pairs, ordered
+// lexicographically (ties towards the lower index, like the brute-force scan of cls3d.cu), REPLICATED in every lane; the
+// surviving leaves of a level-2 node are scanned one leaf per lane into private lists that are then merged.  Children are pruned
+// lane-parallel by their point-to-box distance against the K-th distance (kept when equal: an equally distant point may win the
+// tie), with the same slack as the 3-NN kernel; the bound is seeded from the level-2 node nearest to the query.  Distances use
+// the expression of cls3d.cu's brute-force kernel, so both routes return the same bits.
 __device__ __forceinline__ float point_box_dist2(const float qx, const float qy, const float qz, const Box& b) {
     const float gx = fmaxf(0.f, fmaxf(b.lo.x - qx, qx - b.hi.x));
     const float gy = fmaxf(0.f, fmaxf(b.lo.y - qy, qy - b.hi.y));
@@ -269,6 +269,27 @@ __device__ __forceinline__ bool pair_less(const float d0, const int i0, const fl
     return d0 < d1 || (d0 == d1 && i0 < i1);
 }
 
+// insert (d, id) into a lexicographically sorted K-list that it beats
+template <int K>
+__device__ __forceinline__ void pair_insert(float (&bd)[K], int (&bi)[K], const float d, const int id) {
+#pragma unroll
+    for (int j = K - 1; j > 0; --j) {
+        const bool shift = pair_less(d, id, bd[j - 1], bi[j - 1]);
+        const bool here = !shift && pair_less(d, id, bd[j], bi[j]);
+        if (shift) {
+            bd[j] = bd[j - 1];
+            bi[j] = bi[j - 1];
+        } else if (here) {
+            bd[j] = d;
+            bi[j] = id;
+        }
+    }
+    if (pair_less(d, id, bd[0], bi[0])) {
+        bd[0] = d;
+        bi[0] = id;
+    }
+}
+
 template <int K>
 __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P, const float4* __restrict__ spts,
                                                                           const Box* __restrict__ l1, int n1,
@@ -277,52 +298,84 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
                                                                           const float* __restrict__ points,
                                                                           const int* __restrict__ sample_idx,
                                                                           float* __restrict__ cand_d, int* __restrict__ cand_i) {
+    // ONE CTA PER QUERY: its 8 warps share the level-2 nodes (node i2 belongs to warp i2 % 8).  A query's walk is a chain of
+    // dependent loads (boxes -> leaves -> points) through the ~10-50 level-2 nodes that reach its neighbourhood; with one warp
+    // per query the kernel's duration was that chain (0.4 ms for 800 queries: too few warps to hide it behind each other).
+    __shared__ float s_md[kQueryWarps][K];
+    __shared__ int s_mi[kQueryWarps][K];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x * kQueryWarps + warp;
+    const int s = blockIdx.x;
     if (s >= S) return;
     const int si = sample_idx[s];
     const float qx = points[3 * (size_t)si], qy = points[3 * (size_t)si + 1], qz = points[3 * (size_t)si + 2];
-    float bd[K];
+    float bd[K];  // the K best so far, replicated in every lane
     int bi[K];
 #pragma unroll
     for (int j = 0; j < K; ++j) {
         bd[j] = FLT_MAX;
         bi[j] = INT_MAX;
     }
-    auto scan_leaf = [&](const int leaf) {
-        const int i = leaf * kFan + lane;
-        float d = FLT_MAX;
-        int id = INT_MAX;
-        if (i < P) {
-            const float4 c = spts[i];
-            const float dx = c.x - qx, dy = c.y - qy, dz = c.z - qz;
-            d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-            id = (int)__float_as_uint(c.w);
-        }
-        unsigned m = __ballot_sync(kFull, pair_less(d, id, bd[K - 1], bi[K - 1]));
-        while (m) {
-            const int l = __ffs(m) - 1;
-            m &= m - 1;
-            const float dl = __shfl_sync(kFull, d, l);
-            const int il = __shfl_sync(kFull, id, l);
-            if (!pair_less(dl, il, bd[K - 1], bi[K - 1])) continue;  // the K-th may have improved since the ballot
+    // merge per-lane sorted candidate lists (ld, li) into the replicated list: K rounds of a lexicographic warp minimum over
+    // the lists' heads; a round's winner is inserted if it beats the current K-th, else nothing better is left anywhere
+    auto merge_lane_lists = [&](float (&ld)[K], int (&li)[K]) {
 #pragma unroll
-            for (int j = K - 1; j > 0; --j) {
-                const bool shift = pair_less(dl, il, bd[j - 1], bi[j - 1]);
-                const bool here = !shift && pair_less(dl, il, bd[j], bi[j]);
-                if (shift) {
-                    bd[j] = bd[j - 1];
-                    bi[j] = bi[j - 1];
-                } else if (here) {
-                    bd[j] = dl;
-                    bi[j] = il;
+        for (int r = 0; r < K; ++r) {
+            float hd = ld[0];
+            int hi = li[0];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float od = __shfl_xor_sync(kFull, hd, o);
+                const int oi = __shfl_xor_sync(kFull, hi, o);
+                if (pair_less(od, oi, hd, hi)) {
+                    hd = od;
+                    hi = oi;
                 }
             }
-            if (pair_less(dl, il, bd[0], bi[0])) {
-                bd[0] = dl;
-                bi[0] = il;
+            if (!pair_less(hd, hi, bd[K - 1], bi[K - 1])) break;  // warp-uniform
+            pair_insert<K>(bd, bi, hd, hi);
+            if (hi == li[0] && hd == ld[0]) {  // this lane's head won: pop it (point ids are unique)
+#pragma unroll
+                for (int j = 0; j + 1 < K; ++j) {
+                    ld[j] = ld[j + 1];
+                    li[j] = li[j + 1];
+                }
+                ld[K - 1] = FLT_MAX;
+                li[K - 1] = INT_MAX;
             }
         }
+    };
+    // one LEAF PER LANE: every lane with `mine` walks the 32 points of its own leaf (independent 16-B loads, issued four at a
+    // time) into a private K-list, pre-filtered by the replicated K-th distance; then the 32 lists are merged.  All surviving
+    // leaves of a level-2 node are scanned at once instead of one after the other with one point per lane, which made a query
+    // a chain of ~100 dependent global loads (0.46 ms for 800 queries of 500 k points: as slow as scanning every point).
+    auto scan_leaves = [&](const bool mine, const int leaf) {
+        float ld[K];
+        int li[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            ld[j] = FLT_MAX;
+            li[j] = INT_MAX;
+        }
+        if (mine) {
+            const int base = leaf * kFan;
+            const int cnt = min(kFan, P - base);
+            const float kth = bd[K - 1];
+            const int kth_i = bi[K - 1];
+            for (int k0 = 0; k0 < cnt; k0 += 4) {
+                float4 c[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) c[u] = (k0 + u < cnt) ? __ldg(spts + base + k0 + u) : make_float4(3e18f, 3e18f, 3e18f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float dx = c[u].x - qx, dy = c[u].y - qy, dz = c[u].z - qz;
+                    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                    const int id = (int)__float_as_uint(c[u].w);
+                    if (k0 + u < cnt && pair_less(d, id, kth, kth_i) && pair_less(d, id, ld[K - 1], li[K - 1]))
+                        pair_insert<K>(ld, li, d, id);
+                }
+            }
+        }
+        merge_lane_lists(ld, li);
     };
     // index of the child (of `count` boxes starting at `first`) nearest to the query: lane-parallel, lowest index on ties
     auto nearest_child = [&](const Box* __restrict__ boxes, const int first, const int count) -> int {
@@ -347,11 +400,16 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
         }
         return arg;
     };
+    // seed the bound: the level-2 node nearest to the query, all of its leaves at once
     const int s3 = nearest_child(l3, 0, n3);
-    const int s2 = nearest_child(l2, s3 * kFan, min(kFan, n2 - s3 * kFan));
-    const int seed = nearest_child(l1, s2 * kFan, min(kFan, n1 - s2 * kFan));
-    scan_leaf(seed);
-
+    const int seed2 = nearest_child(l2, s3 * kFan, min(kFan, n2 - s3 * kFan));
+    {
+        const int leaf = seed2 * kFan + lane;
+        scan_leaves(leaf < n1, leaf);
+    }
+    // every warp has scanned the seed node and holds the same K pairs; from here on warp w adds the candidates of ITS level-2
+    // nodes.  The union of the eight lists contains the true K nearest; the seed pairs appear in all of them and are dropped
+    // as duplicates in the final merge (point ids are unique, so equal pairs are the same point).
     const float kSlack = 1.0f - 1e-5f;
     for (int c3 = 0; c3 < n3; c3 += 32) {
         const int i3 = c3 + lane;
@@ -360,28 +418,62 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
             const int b3 = c3 + __ffs(m3) - 1;
             m3 &= m3 - 1;
             const int i2 = b3 * kFan + lane;
-            unsigned m2 = __ballot_sync(kFull, i2 < n2 && !(point_box_dist2(qx, qy, qz, l2[i2 < n2 ? i2 : 0]) * kSlack > bd[K - 1]));
+            unsigned m2 = __ballot_sync(kFull, i2 < n2 && i2 != seed2 && (i2 % kQueryWarps) == warp &&
+                                                   !(point_box_dist2(qx, qy, qz, l2[i2 < n2 ? i2 : 0]) * kSlack > bd[K - 1]));
             while (m2) {
                 const int b2 = b3 * kFan + __ffs(m2) - 1;
                 m2 &= m2 - 1;
-                const int i1 = b2 * kFan + lane;
-                unsigned m1 = __ballot_sync(kFull, i1 < n1 && i1 != seed &&
-                                                       !(point_box_dist2(qx, qy, qz, l1[i1 < n1 ? i1 : 0]) * kSlack > bd[K - 1]));
-                while (m1) {
-                    const int b1 = b2 * kFan + __ffs(m1) - 1;
-                    m1 &= m1 - 1;
-                    if (point_box_dist2(qx, qy, qz, l1[b1]) * kSlack > bd[K - 1]) continue;  // the bound tightened meanwhile
-                    scan_leaf(b1);
-                }
+                if (point_box_dist2(qx, qy, qz, l2[b2]) * kSlack > bd[K - 1]) continue;  // the bound tightened meanwhile
+                const int leaf = b2 * kFan + lane;
+                const bool mine = leaf < n1 && !(point_box_dist2(qx, qy, qz, l1[leaf < n1 ? leaf : 0]) * kSlack > bd[K - 1]);
+                if (__any_sync(kFull, mine)) scan_leaves(mine, leaf);
             }
         }
     }
+    // warps -> block: lanes 0..7 of warp 0 take one warp's list each; K rounds of the lexicographic minimum over the heads, every
+    // lane whose head IS the winner pops it (which also removes the duplicates of the seed pairs)
 #pragma unroll
     for (int j = 0; j < K; ++j)
         if (lane == j) {
-            cand_d[(size_t)s * K + j] = bd[j];
-            cand_i[(size_t)s * K + j] = bi[j];
+            s_md[warp][j] = bd[j];
+            s_mi[warp][j] = bi[j];
         }
+    __syncthreads();
+    if (warp != 0) return;
+    float ld[K];
+    int li[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ld[j] = lane < kQueryWarps ? s_md[lane][j] : FLT_MAX;
+        li[j] = lane < kQueryWarps ? s_mi[lane][j] : INT_MAX;
+    }
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+        float hd = ld[0];
+        int hi = li[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(kFull, hd, o);
+            const int oi = __shfl_xor_sync(kFull, hi, o);
+            if (pair_less(od, oi, hd, hi)) {
+                hd = od;
+                hi = oi;
+            }
+        }
+        if (hi == li[0] && hd == ld[0]) {
+#pragma unroll
+            for (int j = 0; j + 1 < K; ++j) {
+                ld[j] = ld[j + 1];
+                li[j] = li[j + 1];
+            }
+            ld[K - 1] = FLT_MAX;
+            li[K - 1] = INT_MAX;
+        }
+        if (lane == 0) {
+            cand_d[(size_t)s * K + r] = hd;
+            cand_i[(size_t)s * K + r] = hi;
+        }
+    }
 }
 
 struct KnnScratch {
@@ -469,7 +561,7 @@ int knn_tree_query(int K, int P, const void* tree, int S, const float* points, c
                    cudaStream_t stream) {
     if (P <= 0 || S <= 0) return 0;
     KnnScratch s = carve_knn(const_cast<char*>(static_cast<const char*>(tree)), P);
-    const int blocks = ceil_div(S, kQueryWarps);
+    const int blocks = S;  // one CTA per query
     switch (K) {
 #define LSX_KNN_CASE(KK)                                                                                                       \
     case KK:                                                                                                                   \

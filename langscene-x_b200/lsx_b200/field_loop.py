@@ -64,10 +64,10 @@ class LoopConfig:
     reg3d_k: int = 5                     # :119
     reg3d_lambda: float = 4.0            # :120
     reg3d_samples: int = 800
-    # neighbour search of loss_cls_3d through one Morton / box hierarchy per step (lsx_knn_tree_build) instead of a scan of all
-    # points per view: same neighbours; pays from ~1 M Gaussians on (0.64 vs 1.63 ms per call at 2 M with a prebuilt tree), at
-    # LangScene-X's 500 k the scan is as fast as the 800 latency-bound tree walks
-    cls3d_tree: bool = False
+    # neighbour search of loss_cls_3d through one Morton / box hierarchy per step (lsx_knn_tree_build, 0.14 ms at 500 k) and one
+    # CTA per query (knn.cu) instead of a scan of all points per view: the same neighbours bit for bit (tests/test_cls3d.py);
+    # 0.28 vs 0.50 ms per loss call at 500 k, 0.45 vs 1.64 ms at 2 M; a C4-loop view 1.61 vs 1.78 ms (profiles/r6o_*)
+    cls3d_tree: bool = True
     optimise_pose: bool = True           # optim_pose (:67)
     densify_stats: bool = True
     # per-group asynchronous all-reduces issued while the last view's backward is still running, instead of ONE blocking

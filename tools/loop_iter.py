@@ -18,7 +18,7 @@ steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 c = CONFIGS[name]
 dev = torch.device("cuda:0")
 scene = make_scene(c["P"], c["W"], c["H"], F=c["F"], seed=0, s_med=c["s_med"]).to(dev)
-cfg = LoopConfig(cls3d=(name == "C4"))
+cfg = LoopConfig(cls3d=(name == "C4"), cls3d_tree=("tree" in sys.argv[4:]), fused_wrapper=("unfused" not in sys.argv[4:]))
 loop = FieldLoop(bl.make_raw(scene), bl.LRS, torch.zeros(3, device=dev), cfg, n_views=c["views"], poses=bl.make_poses(c["views"], dev))
 views = [bl.make_view(v, c["views"], c["W"], c["H"], c["F"], dev) for v in range(V)]
 si = [bl.sample_indices(v, 0, c["P"], 800, dev) for v in range(V)] if cfg.cls3d else None
