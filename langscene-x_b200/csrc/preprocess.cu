@@ -6,8 +6,14 @@
 //   backward: cuda_rasterizer/backward.cu:20-139 (SH), :144-274 (cov2D), :278-341 (cov3D), :346-396
 //
 // B200 design notes
-//   * one thread per Gaussian, grid sized in whole waves; the forward kernel is a single streaming pass
-//     (HBM-bound: ~332 B in / ~250 B out per Gaussian at the headline config) that ALSO
+//   * one thread per Gaussian and EVERY tensor row is read and written by its owner with 16-B accesses where its alignment
+//     allows: the rows are contiguous per Gaussian (192 B of SH, 64 B of language feature, a 160-B record), so the owner's
+//     accesses use whole sectors and consecutive lanes walk consecutive rows.  (Rounds 1-2 moved the block's slabs through
+//     shared memory with coalesced copies: the cooperative index arithmetic was three quarters of the kernel's instructions
+//     and the 47 KB tile held occupancy at 25 %; per-owner rows are 29 % / 11 % faster, profiles/r6r_*.)  Culled splats read
+//     nothing but their position / covariance inputs;
+//   * the forward kernel is a single streaming pass (HBM-bound: ~332 B in / ~250 B out per visible Gaussian at the
+//     headline config) that ALSO
 //       - zero-fills out_observe (no separate memset),
 //       - emits the 32-bit depth sort key (0xFFFFFFFF for culled splats) for the depth-major presort,
 //       - packs every attribute the tile renderers need into ONE sector-aligned record per Gaussian
@@ -18,7 +24,6 @@
 //     zero-fill traffic at 1M Gaussians.
 //   * arithmetic that feeds radii / tile rects / depth keys keeps the reference's scalar expression
 //     order (including the fp64 island in ndc_to_pix) because those outputs are compared bit-exactly.
-#include "coalesce.cuh"
 #include "head_math.cuh"
 #include "kernels.cuh"
 
@@ -113,22 +118,21 @@ __device__ __forceinline__ void ewa_frame(const float3 mean, const float fx, con
 #define LSX_PRE_BWD_THREADS 128
 #endif
 constexpr int kPreFwdThreads = LSX_PRE_FWD_THREADS;
-// independent 16-B loads in flight per thread while the SH slab is fetched: the whole slab (12 per thread at degree 3) in
-// one round in the forward (C3: 0.190 -> 0.180 ms, C5: 0.88 -> 0.82); the backward is better off with 4 (0.238 vs 0.253)
-constexpr int kFwdSlabDepth = 12, kBwdSlabDepth = 4;
-// smem row stride of the record tile: 16-B aligned rows, and 12 t mod 32 distinct for 8 consecutive t => the
-// row owner's float4 accesses are conflict free
+// smem stride of the threads' record rows: 16-B aligned rows, an odd number of 16-B units => the owners' float4 accesses
+// are conflict free
 __host__ __device__ static inline int record_tile_row(int rec_stride) { return rec_stride + 4; }
 
-// One Gaussian per thread.  `sh_row`: its SH coefficients in shared memory; `rec`: its row of the block's record
-// tile in shared memory, whose feature / map columns have already been filled cooperatively.
+// One Gaussian per thread.  `rec`: the thread's own record row in shared memory (head, colour and pad columns are written here,
+// the caller fills the feature / map columns of visible splats).
 // RAW = the fused render-wrapper mode: `means3D / scales / rotations / opacities` are the reference's raw
 // nn.Parameters (positions, log-scales, un-normalised quaternions, opacity logits), `all_map` is absent, and the wrapper's
 // per-Gaussian work — optional camera-pose transform, exp / normalize / sigmoid, plane normal, all_map (head_math.cuh) — is
 // done here instead of in separate passes over P.  It is a separate instantiation so that the code generated for the
 // reference-shaped mode (whose radii / rects / keys are a bit-exact contract) is untouched.
+// `sh_row` is the Gaussian's row of the (P, M, 3) tensor in global memory, fetched with 16-B loads right before the polynomial
+// (only for splats that survive the culling tests).  Returns whether the splat is visible.
 template <bool RAW>
-__device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p, const int idx, const float* __restrict__ sh_row,
+__device__ __forceinline__ bool preprocess_fwd_row(const PreprocessFwdParams& p, const int idx, const float* __restrict__ sh_row,
                                                    float* __restrict__ rec) {
     // defaults for a culled splat (its record is never read; keep it finite)
     reinterpret_cast<float4*>(rec)[0] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -162,7 +166,7 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
             printf("Point is filtered although prefiltered is set. This shouldn't happen!");
             __trap();
         }
-        return;
+        return false;
     }
 
     const float4 ph = xform_point_4x4(pw, p.proj);
@@ -204,7 +208,7 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
     const float cyy = c2.m[1][1] + 0.3f;
 
     const float det = (cxx * cyy - cxy * cxy);
-    if (det == 0.0f) return;
+    if (det == 0.0f) return false;
     const float det_inv = 1.f / det;
     const float3 conic = make_float3(cyy * det_inv, -cxy * det_inv, cxx * det_inv);
 
@@ -216,7 +220,7 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
     uint2 rmin, rmax;
     tile_rect(pix, (int)my_radius, rmin, rmax, p.grid_x, p.grid_y);
     const uint32_t ntiles = (rmax.x - rmin.x) * (rmax.y - rmin.y);
-    if (ntiles == 0) return;
+    if (ntiles == 0) return false;
 
     // colour: SH evaluation (degrees 0..3) or the caller's precomputed RGB
     float rgb[3];
@@ -227,7 +231,29 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
         // choice), so the packed colour is reproduced bit for bit.
         const float len = sqrtf(__fmaf_rn(dz0, dz0, __fmaf_rn(dx0, dx0, __fmul_rn(dy0, dy0))));
         const float x = dx0 / len, y = dy0 / len, z = dz0 / len;
-        const float* sh = sh_row;
+        float shv[48];  // the coefficients in registers
+        {
+            const int n_sh = p.M * 3;
+#pragma unroll
+            for (int k = 0; k < 48; ++k) shv[k] = 0.f;
+            if ((n_sh & 3) == 0 && (reinterpret_cast<uintptr_t>(sh_row) & 15u) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(sh_row);
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    if (4 * j < n_sh) {
+                        const float4 v = __ldg(s4 + j);
+                        shv[4 * j] = v.x;
+                        shv[4 * j + 1] = v.y;
+                        shv[4 * j + 2] = v.z;
+                        shv[4 * j + 3] = v.w;
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 48; ++k)
+                    if (k < n_sh) shv[k] = __ldg(sh_row + k);
+            }
+        }
+        const float* sh = shv;
         unsigned clamp_bits = 0;
         // direction polynomials shared by the three colour channels
         float b1y = 0.f, b1z = 0.f, b1x = 0.f, b4 = 0.f, b5 = 0.f, b6 = 0.f, b7 = 0.f, b8 = 0.f;
@@ -308,42 +334,67 @@ __device__ __forceinline__ void preprocess_fwd_row(const PreprocessFwdParams& p,
     rec[REC_HEAD + 0] = rgb[0];
     rec[REC_HEAD + 1] = rgb[1];
     rec[REC_HEAD + 2] = rgb[2];
+    return true;
 }
 
-// Block = 128 Gaussians.  SH coefficients in, and the packed blend records out, move through shared memory with
-// coalesced 16-B accesses (coalesce.cuh); language / instance features and the all_map rows are copied
-// cooperatively straight into their columns of the record tile.
+// own-row copy global -> the thread's record row in shared memory
+__device__ __forceinline__ void row_fetch(float* __restrict__ dst, const float* __restrict__ src, const int n) {
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+#pragma unroll 4
+        for (int k = 0; k < n; k += 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(src + k));
+            dst[k] = v.x;
+            dst[k + 1] = v.y;
+            dst[k + 2] = v.z;
+            dst[k + 3] = v.w;
+        }
+    } else {
+#pragma unroll 5
+        for (int k = 0; k < n; ++k) dst[k] = __ldg(src + k);
+    }
+}
+
+// One Gaussian per thread, every tensor row read and written by its owner: the rows of the (P, ...) tensors are contiguous
+// per Gaussian (192 B of SH, 64 B of language feature, a 160-B record), so the owner's 16-B accesses use whole sectors and
+// consecutive lanes walk consecutive rows.  Shared memory only holds the thread's own record row while it is assembled (its
+// column offsets depend on F / Fi at run time): no barrier, no cooperative index arithmetic — that arithmetic was three
+// quarters of the staged version's instructions.  Culled splats read nothing but their position / covariance inputs.
+// 6 blocks of 128 threads per SM: 80 registers (ptxas settles on 86 otherwise); C5 0.621 -> 0.595 ms
+#ifndef LSX_PRE_FWD_MINB
+#define LSX_PRE_FWD_MINB 6
+#endif
 template <bool RAW>
-__global__ void __launch_bounds__(kPreFwdThreads) preprocess_fwd_kernel(const PreprocessFwdParams p) {
+__global__ void __launch_bounds__(kPreFwdThreads, LSX_PRE_FWD_MINB) preprocess_fwd_kernel(const PreprocessFwdParams p) {
     extern __shared__ __align__(16) float s_pre[];
-    const int n_sh = p.M * 3;
-    const int sh_stride = p.shs ? padded_row(n_sh) : 0;  // odd: thread-per-row reads are conflict free
+    const int idx = blockIdx.x * kPreFwdThreads + threadIdx.x;
+    if (idx >= p.P) return;
     const int rec_row = record_tile_row(p.rec_stride);
-    float* s_sh = s_pre;
-    float* s_rec = s_pre + ((kPreFwdThreads * sh_stride + 3) & ~3);
-    const int b0 = blockIdx.x * kPreFwdThreads;
-    const int rows = min(kPreFwdThreads, p.P - b0);
-    if (p.shs && p.colors_precomp == nullptr) slab_load<kPreFwdThreads, kFwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_stride);
+    float* rec = s_pre + threadIdx.x * rec_row;
+    const int n_sh = p.M * 3;
+    const bool visible = preprocess_fwd_row<RAW>(p, idx, p.shs ? p.shs + (size_t)idx * n_sh : nullptr, rec);
+    float4* out = reinterpret_cast<float4*>(p.records + (size_t)idx * p.rec_stride);
+    const int n4 = p.rec_stride >> 2;
+    if (!visible) {  // never read; kept finite
+        for (int j = 0; j < n4; ++j) out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     int c = REC_HEAD + 3;
     if (p.include_feature) {
-        slab_load<kPreFwdThreads>(s_rec + c, p.language_feature + (size_t)b0 * p.F, rows, p.F, rec_row);
+        row_fetch(rec + c, p.language_feature + (size_t)idx * p.F, p.F);
         c += p.F;
-        slab_load<kPreFwdThreads>(s_rec + c, p.language_feature_instance + (size_t)b0 * p.Fi, rows, p.Fi, rec_row);
+        row_fetch(rec + c, p.language_feature_instance + (size_t)idx * p.Fi, p.Fi);
         c += p.Fi;
     }
-    if (!RAW && p.render_geo) slab_load<kPreFwdThreads>(s_rec + c, p.all_map + (size_t)b0 * 5, rows, 5, rec_row);
-    __syncthreads();
-    if ((int)threadIdx.x < rows)
-        preprocess_fwd_row<RAW>(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_stride, s_rec + threadIdx.x * rec_row);
-    __syncthreads();
-    slab_store<kPreFwdThreads>(p.records + (size_t)b0 * p.rec_stride, s_rec, rows, p.rec_stride, rec_row);
+    if (!RAW && p.render_geo) row_fetch(rec + c, p.all_map + (size_t)idx * 5, 5);
+    for (int j = 0; j < n4; ++j) out[j] = reinterpret_cast<const float4*>(rec)[j];
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward (K8 + K9 fused): dL/dconic, dL/dmean2D, dL/dcolor  ->  dL/d{mean3D, cov3D, sh, scale, rot}
 // ------------------------------------------------------------------------------------------------
-// One Gaussian per thread.  `sh_row` is this Gaussian's SH coefficients in shared memory (read) and is overwritten
-// with dL/dsh at the end; `grec` is its packed gradient record from the tile backward pass (render_bwd.cu):
+// One Gaussian per thread.  `sh_row` is this Gaussian's row of the (P, M, 3) tensor in global memory (read with 16-B loads, by
+// visible splats only; dL/dsh goes straight from registers to the row's place in p.dL_dsh); `grec` is its packed gradient
+// record from the tile backward pass (render_bwd.cu):
 // [rgb(3) | language(F) | instance(Fi) | all_map(5) | pad | mean2D.xy, |mean2D|.xy, conic.xyw, opacity].
 // Culled splats have an all-zero record (memset, never accumulated into).
 constexpr int kPreBwdThreads = LSX_PRE_BWD_THREADS;
@@ -353,11 +404,12 @@ constexpr int kPreBwdThreads = LSX_PRE_BWD_THREADS;
 // plane normal, all_map, optional camera pose) and arrive in dL_dmeans3D / dL_dscales / dL_drotations / dL_dopacity as
 // gradients of the RAW parameters; `pose_acc` collects this row's 16 pose-gradient terms.
 template <bool RAW>
-__device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, float* __restrict__ sh_row,
+__device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p, const int idx, const float* __restrict__ sh_row,
                                                    const float (&grec)[3], const float (&ggeo)[8], const float (&gmap)[5],
                                                    float (&pose_acc)[kPoseTerms]) {
     const int n_sh = p.M * 3;
-    float* g_sh = p.dL_dsh ? sh_row : nullptr;
+    float* dsh_out = (p.dL_dsh && p.shs) ? p.dL_dsh + (size_t)idx * n_sh : nullptr;
+    const bool dsh_vec = (n_sh & 3) == 0 && (reinterpret_cast<uintptr_t>(dsh_out) & 15u) == 0;
     p.dL_dmean2D[3 * idx + 0] = ggeo[0];
     p.dL_dmean2D[3 * idx + 1] = ggeo[1];
     p.dL_dmean2D[3 * idx + 2] = 0.f;
@@ -388,8 +440,13 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
             for (int i = 0; i < 3; ++i) p.dL_dscales[3 * idx + i] = 0.f;
         }
         if (!(am & LSX_ACC_ROTATIONS)) reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g_sh)
-            for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
+        if (dsh_out && !(p.accumulate & LSX_ACC_SH)) {
+            if (dsh_vec) {
+                for (int i = 0; i < n_sh; i += 4) *reinterpret_cast<float4*>(dsh_out + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = 0; i < n_sh; ++i) dsh_out[i] = 0.f;
+            }
+        }
         return;
     }
 
@@ -518,7 +575,30 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         const float ox = mean.x - p.campos[0], oy = mean.y - p.campos[1], oz = mean.z - p.campos[2];
         const float len = sqrtf(ox * ox + oy * oy + oz * oz);
         const float x = ox / len, y = oy / len, z = oz / len;
-        const float* sh = sh_row;
+        float shv[48];  // the coefficients in registers
+        {
+#pragma unroll
+            for (int k = 0; k < 48; ++k) shv[k] = 0.f;
+            if (p.D > 0) {  // only the direction gradient reads coefficients
+                if ((n_sh & 3) == 0 && (reinterpret_cast<uintptr_t>(sh_row) & 15u) == 0) {
+                    const float4* s4 = reinterpret_cast<const float4*>(sh_row);
+#pragma unroll
+                    for (int j = 0; j < 12; ++j)
+                        if (4 * j < n_sh) {
+                            const float4 v = __ldg(s4 + j);
+                            shv[4 * j] = v.x;
+                            shv[4 * j + 1] = v.y;
+                            shv[4 * j + 2] = v.z;
+                            shv[4 * j + 3] = v.w;
+                        }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 48; ++k)
+                        if (k < n_sh) shv[k] = __ldg(sh_row + k);
+                }
+            }
+        }
+        const float* sh = shv;
         const unsigned cl = p.clamped[idx];
         float gc[3];
 #pragma unroll
@@ -583,10 +663,29 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
                 }
             }
         }
-        for (int j = 0; j < p.M; ++j) {
-            const float bj = (j < nb) ? basis[j < 16 ? j : 15] : 0.f;
+        {
+            if (dsh_out) {
+                // element e = 3 j + k of the row is basis[j] * gc[k] (zero beyond the active degree)
+                auto elem = [&](const int e) -> float {
+                    const int j = e / 3, k = e - 3 * j;
+                    return (j < nb) ? basis[j] * gc[k] : 0.f;
+                };
+                const bool acc = (p.accumulate & LSX_ACC_SH) != 0;
+                if (dsh_vec) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) g_sh[3 * j + k] = (j < nb) ? bj * gc[k] : 0.f;
+                    for (int i = 0; i < 12; ++i)
+                        if (4 * i < n_sh) {
+                            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (acc) o = *reinterpret_cast<const float4*>(dsh_out + 4 * i);
+                            *reinterpret_cast<float4*>(dsh_out + 4 * i) =
+                                make_float4(o.x + elem(4 * i), o.y + elem(4 * i + 1), o.z + elem(4 * i + 2), o.w + elem(4 * i + 3));
+                        }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 48; ++e)
+                        if (e < n_sh) dsh_out[e] = acc ? dsh_out[e] + elem(e) : elem(e);
+                }
+            }
         }
 
         // direction gradient, then through the normalisation dir = v / |v|
@@ -598,8 +697,6 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
         g_mean.x += ((+sum2 - ox * ox) * gdx - oy * ox * gdy - oz * ox * gdz) * inv32;
         g_mean.y += (-ox * oy * gdx + (sum2 - oy * oy) * gdy - oz * oy * gdz) * inv32;
         g_mean.z += (-ox * oz * gdx - oy * oz * gdy + (sum2 - oz * oz) * gdz) * inv32;
-    } else if (g_sh) {
-        for (int i = 0; i < n_sh; ++i) g_sh[i] = 0.f;
     }
 
     if constexpr (!RAW) {
@@ -712,27 +809,41 @@ __device__ __forceinline__ void preprocess_bwd_row(const PreprocessBwdParams& p,
     }
 }
 
-// Block = 128 Gaussians.  The SH slab and the gradient-record slab of the block are moved through shared memory
-// with coalesced 16-B accesses (coalesce.cuh); dL/dsh and the unpacked colour / feature / map gradients leave the
-// same way.  Every output row is written exactly once (zeros for culled splats).
-#ifndef LSX_PRE_BWD_RAW_MINBLOCKS
-#define LSX_PRE_BWD_RAW_MINBLOCKS 1
+// own-row copy of `n` record columns -> the row of a (P, n) gradient tensor (accumulate: +=)
+__device__ __forceinline__ void row_put(float* __restrict__ dst, const float* __restrict__ src, const int n, const bool acc) {
+    if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+#pragma unroll 4
+        for (int k = 0; k < n; k += 4) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (acc) o = *reinterpret_cast<const float4*>(dst + k);
+            *reinterpret_cast<float4*>(dst + k) =
+                make_float4(o.x + __ldg(src + k), o.y + __ldg(src + k + 1), o.z + __ldg(src + k + 2), o.w + __ldg(src + k + 3));
+        }
+    } else {
+#pragma unroll 5
+        for (int k = 0; k < n; ++k) dst[k] = acc ? dst[k] + __ldg(src + k) : __ldg(src + k);
+    }
+}
+#ifndef LSX_PRE_BWD_MINB
+#define LSX_PRE_BWD_MINB 0
 #endif
+#ifndef LSX_PRE_BWD_MINB_RAW
+#define LSX_PRE_BWD_MINB_RAW 0
+#endif
+// One Gaussian per thread, every row read and written by its owner (see the forward kernel): the gradient record's columns go
+// to the rows of the reference's gradient tensors, dL/dsh goes from registers to its row.  No shared-memory slab: the block
+// only meets for the pose-gradient partial sums of the fused-wrapper mode.
 template <bool RAW>
-__global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_RAW_MINBLOCKS : 1) preprocess_bwd_kernel(const PreprocessBwdParams p) {
-    extern __shared__ __align__(16) float s_pre[];
+__global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_MINB_RAW : LSX_PRE_BWD_MINB) preprocess_bwd_kernel(const PreprocessBwdParams p) {
     const int n_sh = p.M * 3;
-    const int sh_row = padded_row(n_sh);
-    float* s_sh = s_pre;
-    const int b0 = blockIdx.x * kPreBwdThreads;
-    const int rows = min(kPreBwdThreads, p.P - b0);
+    const int idx = blockIdx.x * kPreBwdThreads + threadIdx.x;
     const unsigned am = (unsigned)p.accumulate;
-    const float* rec0 = p.grad_records + (size_t)b0 * p.grad_stride;
-    // the thread's own colour gradient and 8 geometry terms, straight from its record (16-B aligned: both offsets are
-    // multiples of 4 floats)
-    float gcol[3] = {0.f, 0.f, 0.f}, ggeo[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gmap[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if ((int)threadIdx.x < rows) {
-        const float* rec = rec0 + (size_t)threadIdx.x * p.grad_stride;
+    float pose_acc[kPoseTerms];
+#pragma unroll
+    for (int k = 0; k < kPoseTerms; ++k) pose_acc[k] = 0.f;
+    if (idx < p.P) {
+        const float* rec = p.grad_records + (size_t)idx * p.grad_stride;
+        float gcol[3], ggeo[8], gmap[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
         if (RAW && p.render_geo) {  // the all_map gradient goes on through the wrapper's backward instead of out
             const int cm = 3 + (p.include_feature ? p.F + p.Fi : 0);
 #pragma unroll
@@ -746,33 +857,24 @@ __global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_RAW_MINBLOCK
         ggeo[4] = g1.x; ggeo[5] = g1.y; ggeo[6] = g1.z; ggeo[7] = g1.w;
         ggeo[0] *= p.geo_scale_x; ggeo[1] *= p.geo_scale_y; ggeo[2] *= p.geo_scale_x; ggeo[3] *= p.geo_scale_y;
         ggeo[4] *= -0.5f; ggeo[5] *= -0.5f; ggeo[6] *= -0.5f;
-    }
-    if (p.shs) slab_load<kPreBwdThreads, kBwdSlabDepth>(s_sh, p.shs + (size_t)b0 * n_sh, rows, n_sh, sh_row);
-    // The blended channels' gradients leave the records unchanged: copied record columns -> the reference's tensors with
-    // coalesced 16-B stores, no shared-memory tile (the tile cost 19 KB per block and with it 3 of 8 resident blocks).
-    slab_copy_columns<kPreBwdThreads>(p.dL_dcolor + (size_t)b0 * 3, rec0, rows, 3, p.grad_stride, 0, (am & LSX_ACC_COLORS) != 0);
-    int c = 3;
-    if (p.include_feature) {
-        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature + (size_t)b0 * p.F, rec0, rows, p.F, p.grad_stride, c,
-                                          (am & LSX_ACC_LANG) != 0);
-        c += p.F;
-        slab_copy_columns<kPreBwdThreads>(p.dL_dlanguage_feature_instance + (size_t)b0 * p.Fi, rec0, rows, p.Fi, p.grad_stride, c,
-                                          (am & LSX_ACC_INST) != 0);
-        c += p.Fi;
-    }
-    if (RAW && p.dL_dall_map == nullptr) {
-        // raw mode: all_map is not an input of the call, its gradient is consumed by preprocess_bwd_row
-    } else if (p.render_geo) {
-        slab_copy_columns<kPreBwdThreads>(p.dL_dall_map + (size_t)b0 * 5, rec0, rows, 5, p.grad_stride, c, (am & LSX_ACC_ALL_MAP) != 0);
-    } else if (!(am & LSX_ACC_ALL_MAP)) {
-        for (int e = threadIdx.x; e < rows * 5; e += kPreBwdThreads) p.dL_dall_map[(size_t)b0 * 5 + e] = 0.f;
-    }
-    __syncthreads();
-    float pose_acc[kPoseTerms];
+        row_put(p.dL_dcolor + (size_t)idx * 3, rec, 3, (am & LSX_ACC_COLORS) != 0);
+        int c = 3;
+        if (p.include_feature) {
+            row_put(p.dL_dlanguage_feature + (size_t)idx * p.F, rec + c, p.F, (am & LSX_ACC_LANG) != 0);
+            c += p.F;
+            row_put(p.dL_dlanguage_feature_instance + (size_t)idx * p.Fi, rec + c, p.Fi, (am & LSX_ACC_INST) != 0);
+            c += p.Fi;
+        }
+        if (RAW && p.dL_dall_map == nullptr) {
+            // raw mode: all_map is not an input of the call, its gradient is consumed by preprocess_bwd_row
+        } else if (p.render_geo) {
+            row_put(p.dL_dall_map + (size_t)idx * 5, rec + c, 5, (am & LSX_ACC_ALL_MAP) != 0);
+        } else if (!(am & LSX_ACC_ALL_MAP)) {
 #pragma unroll
-    for (int k = 0; k < kPoseTerms; ++k) pose_acc[k] = 0.f;
-    if ((int)threadIdx.x < rows)
-        preprocess_bwd_row<RAW>(p, b0 + threadIdx.x, s_sh + threadIdx.x * sh_row, gcol, ggeo, gmap, pose_acc);
+            for (int k = 0; k < 5; ++k) p.dL_dall_map[(size_t)idx * 5 + k] = 0.f;
+        }
+        preprocess_bwd_row<RAW>(p, idx, p.shs ? p.shs + (size_t)idx * n_sh : nullptr, gcol, ggeo, gmap, pose_acc);
+    }
     if (RAW && p.pose != nullptr && p.pose_partials != nullptr) {
         // this block's row of pose-gradient partial sums (fixed order: deterministic); lsx::launch_pose_finish adds the rows
         __shared__ float s_pose[kPreBwdThreads / 32][kPoseTerms];
@@ -792,8 +894,6 @@ __global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_RAW_MINBLOCK
             p.pose_partials[(size_t)blockIdx.x * kPoseTerms + threadIdx.x] = v;
         }
     }
-    __syncthreads();
-    if (p.dL_dsh && p.shs) slab_store<kPreBwdThreads>(p.dL_dsh + (size_t)b0 * n_sh, s_sh, rows, n_sh, sh_row, 0, (am & LSX_ACC_SH) != 0);
 }
 
 __global__ void __launch_bounds__(256) mark_visible_kernel(int P, const float* __restrict__ means3D,
@@ -826,10 +926,7 @@ static cudaError_t ensure_dynamic_smem(const void* func, size_t bytes, int slot)
 
 int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
-    const int n_sh = p.M * 3;
-    const int sh_stride = p.shs ? padded_row(n_sh) : 0;
-    const size_t smem = ((size_t)((kPreFwdThreads * sh_stride + 3) & ~3) + (size_t)kPreFwdThreads * record_tile_row(p.rec_stride)) *
-                        sizeof(float);
+    const size_t smem = (size_t)kPreFwdThreads * record_tile_row(p.rec_stride) * sizeof(float);  // the threads' record rows
     if (p.raw_params) {
         LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_fwd_kernel<true>), smem, 2));
         preprocess_fwd_kernel<true><<<ceil_div(p.P, kPreFwdThreads), kPreFwdThreads, smem, stream>>>(p);
@@ -843,7 +940,7 @@ int launch_preprocess_fwd(const PreprocessFwdParams& p, cudaStream_t stream, boo
 
 int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, bool debug) {
     if (p.P <= 0) return 0;
-    const size_t smem = (size_t)kPreBwdThreads * (p.shs ? padded_row(p.M * 3) : 0) * sizeof(float);
+    const size_t smem = 0;
     const int blocks = ceil_div(p.P, kPreBwdThreads);
     if (p.raw_params) {
         LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel<true>), smem, 3));

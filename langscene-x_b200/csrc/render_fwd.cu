@@ -24,6 +24,13 @@
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
+#ifndef LSX_FWD_FFMA2
+#define LSX_FWD_FFMA2 0
+#endif
+#ifndef LSX_FWD_MINB
+#define LSX_FWD_MINB 0
+#endif
+
 namespace lsx {
 
 namespace {
@@ -31,7 +38,7 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 template <int CT4>
-__global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(32, LSX_FWD_MINB) render_fwd_kernel(const RenderParams p) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     using Stage = ListStage<RS>;
     constexpr int CHUNK = Stage::CHUNK;
@@ -57,9 +64,15 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
     float T = inside ? 1.0f : 0.0f;
     float T_final = 1.0f;
     uint32_t last_k = 0;  // elements of the compacted list up to and including this pixel's last contributor
+#if LSX_FWD_FFMA2
+    f32x2 acc2[CT4 / 2];  // channels (2 j, 2 j + 1)
+#pragma unroll
+    for (int j = 0; j < CT4 / 2; ++j) acc2[j] = 0ull;
+#else
     float acc[CT4];
 #pragma unroll
     for (int c = 0; c < CT4; ++c) acc[c] = 0.f;
+#endif
 
     Stage stage;
     const bool any_live = !__all_sync(kFull, T == 0.0f);
@@ -89,6 +102,13 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
                 if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
                 if (blend) {
                     const float w = alpha * T;
+#if LSX_FWD_FFMA2
+                    const f32x2 w2 = pack2(w, w);
+                    f32x2 f[CT4 / 2];
+                    lds_row_pairs<CT4 / 4>(ra + REC_HEAD * 4, f);
+#pragma unroll
+                    for (int j = 0; j < CT4 / 2; ++j) acc2[j] = fma2(f[j], w2, acc2[j]);
+#else
                     float4 f[CT4 / 4];
                     lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
 #pragma unroll
@@ -98,6 +118,7 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
                         acc[4 * q + 2] += f[q].z * w;
                         acc[4 * q + 3] += f[q].w * w;
                     }
+#endif
                     T = test_T;
                     last_k = (uint32_t)(r * CHUNK + s_ + 1);
                 }
@@ -109,6 +130,15 @@ __global__ void __launch_bounds__(32) render_fwd_kernel(const RenderParams p) {
         stage.drain();  // never leave with copies still in flight into this CTA's shared memory
     }
     if (T != 0.0f) T_final = T;  // never terminated
+#if LSX_FWD_FFMA2
+    float acc[CT4];
+#pragma unroll
+    for (int j = 0; j < CT4 / 2; ++j) {
+        const float2 a = unpack2(acc2[j]);
+        acc[2 * j] = a.x;
+        acc[2 * j + 1] = a.y;
+    }
+#endif
 
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
