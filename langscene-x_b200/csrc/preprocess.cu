@@ -374,10 +374,8 @@ __global__ void __launch_bounds__(kPreFwdThreads, LSX_PRE_FWD_MINB) preprocess_f
     const bool visible = preprocess_fwd_row<RAW>(p, idx, p.shs ? p.shs + (size_t)idx * n_sh : nullptr, rec);
     float4* out = reinterpret_cast<float4*>(p.records + (size_t)idx * p.rec_stride);
     const int n4 = p.rec_stride >> 2;
-    if (!visible) {  // never read; kept finite
-        for (int j = 0; j < n4; ++j) out[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
+    // a culled splat has no list entry (tiles_touched = 0), so nothing ever reads its record: it is not written
+    if (!visible) return;
     int c = REC_HEAD + 3;
     if (p.include_feature) {
         row_fetch(rec + c, p.language_feature + (size_t)idx * p.F, p.F);

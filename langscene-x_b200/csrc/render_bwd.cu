@@ -36,7 +36,11 @@
 //     (32-pixel block, Gaussian), all into one contiguous 144-B record.
 //   * warp-ballot skip of entries no lane blends.
 //
-// Tried and dropped in round 2 (commit 35841d2, profiles/r6c_bwd_transposed_ab.jsonl): the TRANSPOSED formulation — lane =
+// Tried and dropped in round 2: packed FFMA2 for the dot product and the outer product (30 fewer issue slots of 193 per blended
+// visit, 2.013 -> 1.987 ms: within noise — shared-memory wavefronts, 80 % of the L1 peak, and latency bound this kernel, not
+// issue slots alone); contiguous-piece and bulk-copy (one 160-B cp.async.bulk per record + mbarrier) staging instead of the
+// two-lanes-per-record LDGSTS, whose 16-B pieces each cost a wavefront: 2.23 / 2.08 ms (profiles/r6p_*_ab.log).
+// Also (commit 35841d2, profiles/r6c_bwd_transposed_ab.jsonl): the TRANSPOSED formulation — lane =
 // list entry with its record in registers, the 32 pixels walked in a loop, channel and geometry gradients accumulated in
 // registers (no exchange, 16 instead of 53 shared-memory wavefronts per visit), the per-pixel recurrences turned into two
 // warp scans.  Bit-for-bit the same parity tier (34 / 34 tests), the same ~165 instructions per 32 (pixel, entry) pairs, but
@@ -44,10 +48,6 @@
 // registers) leave the schedulers idle — this kernel is bound by issue slots AND latency, not by shared memory alone.
 #include "kernels.cuh"
 #include "tile_stage.cuh"
-
-#ifndef LSX_BWD_FFMA2
-#define LSX_BWD_FFMA2 0
-#endif
 
 namespace lsx {
 
@@ -160,12 +160,7 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
     if (n_eff == 0) return;
 
     // ---- transposed view: gT[ps][q] = upstream gradient of channel (32 ps + lane) at pixel q of this block ----
-#if LSX_BWD_FFMA2
-    f32x2 gT2[NPASS][16];  // pixels (2 j, 2 j + 1)
-    f32x2 g2[CT4 / 2];     // channels (2 j, 2 j + 1) of this pixel
-#else
     float gT[NPASS][32];
-#endif
     {
         float* ts = reinterpret_cast<float*>(smem_raw);  // aliases the record buffers (not yet live)
 #pragma unroll
@@ -174,23 +169,10 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int c = ps * 32 + (int)lane;
-#if LSX_BWD_FFMA2
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float lo = (c < CT4) ? ts[(2 * j) * TS + c] : ((c < CT4 + NGL) ? 1.0f : 0.f);
-                const float hi = (c < CT4) ? ts[(2 * j + 1) * TS + c] : ((c < CT4 + NGL) ? 1.0f : 0.f);
-                gT2[ps][j] = pack2(lo, hi);
-            }
-#else
 #pragma unroll
             for (int q = 0; q < 32; ++q) gT[ps][q] = (c < CT4) ? ts[q * TS + c] : ((c < CT4 + NGL) ? 1.0f : 0.f);
-#endif
         }
         __syncwarp();
-#if LSX_BWD_FFMA2
-#pragma unroll
-        for (int j = 0; j < CT4 / 2; ++j) g2[j] = pack2(g[2 * j], g[2 * j + 1]);
-#endif
     }
     // which exchanged array this lane sums in the outer-product phase: 0 = weights, 1 + k = geometry term k
     const uint32_t my_array = ((int)lane >= CT4 && (int)lane < CT4 + NGL) ? (1u + lane - CT4) : 0u;
@@ -247,18 +229,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
                 float rcp;
                 asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(om));
                 const float Tn = T * rcp;
-#if LSX_BWD_FFMA2
-                f32x2 s01 = 0ull, s23 = 0ull;
-#pragma unroll
-                for (int q = 0; q < CT4 / 4; ++q) {
-                    f32x2 f[2];
-                    lds128xN_pairs<1>(ra + REC_HEAD * 4 + q * 16, f);
-                    s01 = fma2(f[0], g2[2 * q], s01);
-                    s23 = fma2(f[1], g2[2 * q + 1], s23);
-                }
-                const float2 sa = unpack2(s01), sb = unpack2(s23);
-                const float s = (sa.x + sa.y) + (sb.x + sb.y);
-#else
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int q = 0; q < CT4 / 4; ++q) {
@@ -269,7 +239,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
                     s3 += f.w * g[4 * q + 3];
                 }
                 const float s = (s0 + s1) + (s2 + s3);
-#endif
                 const float dL_dalpha = (s - Bacc) * Tn - Tf_bg * rcp;
                 w = blend ? alpha * Tn : 0.f;
                 u = blend ? G * dL_dalpha : 0.f;
@@ -299,31 +268,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
             }
             const uint32_t wl = wa + my_array * (uint32_t)(XROW * 4);
             float cg[NPASS][4];
-#if LSX_BWD_FFMA2
-            {
-                f32x2 c01[NPASS], c23[NPASS];
-#pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) c01[ps] = c23[ps] = 0ull;
-#pragma unroll
-                for (int q4 = 0; q4 < 8; ++q4) {
-                    f32x2 wq[2];
-                    lds128xN_pairs<1>(wl + q4 * 16, wq);
-#pragma unroll
-                    for (int ps = 0; ps < NPASS; ++ps) {
-                        c01[ps] = fma2(wq[0], gT2[ps][2 * q4], c01[ps]);
-                        c23[ps] = fma2(wq[1], gT2[ps][2 * q4 + 1], c23[ps]);
-                    }
-                }
-#pragma unroll
-                for (int ps = 0; ps < NPASS; ++ps) {
-                    const float2 a = unpack2(c01[ps]), b = unpack2(c23[ps]);
-                    cg[ps][0] = a.x;
-                    cg[ps][1] = a.y;
-                    cg[ps][2] = b.x;
-                    cg[ps][3] = b.y;
-                }
-            }
-#else
 #pragma unroll
             for (int ps = 0; ps < NPASS; ++ps) cg[ps][0] = cg[ps][1] = cg[ps][2] = cg[ps][3] = 0.f;
 #pragma unroll
@@ -337,7 +281,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
                     cg[ps][3] += wq.w * gT[ps][4 * q4 + 3];
                 }
             }
-#endif
             LSX_CHECK_INDEX(lds32i(ia), p.P, "gradient record");
             float* grec = p.grad_records + (size_t)lds32i(ia) * GS;
 #pragma unroll

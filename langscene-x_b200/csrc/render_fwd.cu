@@ -24,12 +24,6 @@
 #include "kernels.cuh"
 #include "tile_stage.cuh"
 
-#ifndef LSX_FWD_FFMA2
-#define LSX_FWD_FFMA2 0
-#endif
-#ifndef LSX_FWD_MINB
-#define LSX_FWD_MINB 0
-#endif
 
 namespace lsx {
 
@@ -37,8 +31,14 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+// At 24 / 28 blended channels the accumulation runs on packed pairs (FFMA2: two fp32 FMAs per issue slot, each rounded like
+// fmaf, so the image does not change): the kernel is bound by instruction issue and the FMAs are 40 % of a blended visit.
+// C3 (27 channels): 0.909 -> 0.851 ms; at 16 channels the packed form is 3 % slower (profiles/r6p_ffma2_ab.log), so the
+// narrower instantiations keep the scalar form (and the wider ones, which would spill at 64 registers).  32 CTAs / SM are
+// requested for the packed form: ptxas otherwise settles on 78 registers instead of the 64 that fit.
 template <int CT4>
-__global__ void __launch_bounds__(32, LSX_FWD_MINB) render_fwd_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(32, (CT4 == 24 || CT4 == 28) ? 32 : 0) render_fwd_kernel(const RenderParams p) {
+    constexpr bool kPacked = (CT4 == 24 || CT4 == 28);
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     using Stage = ListStage<RS>;
     constexpr int CHUNK = Stage::CHUNK;
@@ -64,15 +64,12 @@ __global__ void __launch_bounds__(32, LSX_FWD_MINB) render_fwd_kernel(const Rend
     float T = inside ? 1.0f : 0.0f;
     float T_final = 1.0f;
     uint32_t last_k = 0;  // elements of the compacted list up to and including this pixel's last contributor
-#if LSX_FWD_FFMA2
-    f32x2 acc2[CT4 / 2];  // channels (2 j, 2 j + 1)
-#pragma unroll
-    for (int j = 0; j < CT4 / 2; ++j) acc2[j] = 0ull;
-#else
+    f32x2 acc2[kPacked ? CT4 / 2 : 1];  // kPacked: channels (2 j, 2 j + 1)
     float acc[CT4];
 #pragma unroll
+    for (int j = 0; j < (kPacked ? CT4 / 2 : 1); ++j) acc2[j] = 0ull;
+#pragma unroll
     for (int c = 0; c < CT4; ++c) acc[c] = 0.f;
-#endif
 
     Stage stage;
     const bool any_live = !__all_sync(kFull, T == 0.0f);
@@ -102,23 +99,23 @@ __global__ void __launch_bounds__(32, LSX_FWD_MINB) render_fwd_kernel(const Rend
                 if (om != 0 && lane == 0) atomicAdd(&p.out_observe[lds32i(ia)], __popc(om));
                 if (blend) {
                     const float w = alpha * T;
-#if LSX_FWD_FFMA2
-                    const f32x2 w2 = pack2(w, w);
-                    f32x2 f[CT4 / 2];
-                    lds_row_pairs<CT4 / 4>(ra + REC_HEAD * 4, f);
+                    if constexpr (kPacked) {
+                        const f32x2 w2 = pack2(w, w);
+                        f32x2 f[CT4 / 2];
+                        lds_row_pairs<CT4 / 4>(ra + REC_HEAD * 4, f);
 #pragma unroll
-                    for (int j = 0; j < CT4 / 2; ++j) acc2[j] = fma2(f[j], w2, acc2[j]);
-#else
-                    float4 f[CT4 / 4];
-                    lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
+                        for (int j = 0; j < CT4 / 2; ++j) acc2[j] = fma2(f[j], w2, acc2[j]);
+                    } else {
+                        float4 f[CT4 / 4];
+                        lds_row<CT4 / 4>(ra + REC_HEAD * 4, f);
 #pragma unroll
-                    for (int q = 0; q < CT4 / 4; ++q) {
-                        acc[4 * q + 0] += f[q].x * w;
-                        acc[4 * q + 1] += f[q].y * w;
-                        acc[4 * q + 2] += f[q].z * w;
-                        acc[4 * q + 3] += f[q].w * w;
+                        for (int q = 0; q < CT4 / 4; ++q) {
+                            acc[4 * q + 0] += f[q].x * w;
+                            acc[4 * q + 1] += f[q].y * w;
+                            acc[4 * q + 2] += f[q].z * w;
+                            acc[4 * q + 3] += f[q].w * w;
+                        }
                     }
-#endif
                     T = test_T;
                     last_k = (uint32_t)(r * CHUNK + s_ + 1);
                 }
@@ -130,15 +127,14 @@ __global__ void __launch_bounds__(32, LSX_FWD_MINB) render_fwd_kernel(const Rend
         stage.drain();  // never leave with copies still in flight into this CTA's shared memory
     }
     if (T != 0.0f) T_final = T;  // never terminated
-#if LSX_FWD_FFMA2
-    float acc[CT4];
+    if constexpr (kPacked) {
 #pragma unroll
-    for (int j = 0; j < CT4 / 2; ++j) {
-        const float2 a = unpack2(acc2[j]);
-        acc[2 * j] = a.x;
-        acc[2 * j + 1] = a.y;
+        for (int j = 0; j < CT4 / 2; ++j) {
+            const float2 a = unpack2(acc2[j]);
+            acc[2 * j] = a.x;
+            acc[2 * j + 1] = a.y;
+        }
     }
-#endif
 
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
