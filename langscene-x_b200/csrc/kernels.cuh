@@ -179,7 +179,7 @@ size_t knn_temp_bytes(int P);
 int knn_mean_dist2(int P, const float* points, float* out, void* temp, cudaStream_t stream);
 // the search structure alone (Morton order, float4 stream, 3-level boxes) into `temp` (knn_temp_bytes(P) bytes), and exact
 // K-nearest queries of S dataset points against it: cand_d / cand_i [S][K] sorted by (distance, index)
-int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream);
+int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream, bool with_rank = true);
 int knn_tree_query(int K, int P, const void* tree, int S, const float* points, const int* sample_idx, float* cand_d, int* cand_i,
                    cudaStream_t stream);
 

@@ -99,12 +99,15 @@ __global__ void __launch_bounds__(256) morton_kernel(int P, const float* __restr
     codes[i] = x | (y << 1) | (z << 2);
 }
 
+// `rank` (optional): position of every original point in the sorted stream (the K-NN queries start from their own leaf)
 __global__ void __launch_bounds__(256) gather_points_kernel(int P, const float* __restrict__ pts,
-                                                            const uint32_t* __restrict__ order, float4* __restrict__ spts) {
+                                                            const uint32_t* __restrict__ order, float4* __restrict__ spts,
+                                                            uint32_t* __restrict__ rank) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P) return;
     const uint32_t i = order[k];
     spts[k] = make_float4(pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2], __uint_as_float(i));
+    if (rank != nullptr) rank[i] = (uint32_t)k;
 }
 
 // ---- box hierarchy -------------------------------------------------------------------------------------
@@ -252,12 +255,20 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_query_kernel(int P, cons
 }
 
 // ---- K nearest points of arbitrary dataset points (loss_cls_3d's neighbour search) -------------------------------------
-// One CTA per query, its warps sharing the level-2 nodes.  Each warp keeps its K best (distance, original index) pairs, ordered
-// lexicographically (ties towards the lower index, like the brute-force scan of cls3d.cu), REPLICATED in every lane; the
-// surviving leaves of a level-2 node are scanned one leaf per lane into private lists that are then merged.  Children are pruned
-// lane-parallel by their point-to-box distance against the K-th distance (kept when equal: an equally distant point may win the
-// tie), with the same slack as the 3-NN kernel; the bound is seeded from the level-2 node nearest to the query.  Distances use
-// the expression of cls3d.cu's brute-force kernel, so both routes return the same bits.
+// One CTA (8 warps) per query, in two phases around a FIXED pruning bound:
+//   seed     warp 0 scans the 32 leaves (one leaf per lane) of the level-2 node that holds the query's own position in the Morton
+//            order and publishes the K best (distance, index) pairs; the K-th is the bound of everything that follows;
+//   collect  the warps share the level-3 nodes; children are pruned lane-parallel by their point-to-box distance against the
+//            bound (kept when equal: an equally distant point may win the tie; same slack as the 3-NN kernel) and the surviving
+//            LEAVES are appended to a queue in shared memory — no leaf is scanned yet, nothing depends on a scan's result;
+//   scan     the queue is scanned 32 leaves at a time, one leaf per lane into that lane's private sorted K-list (16-B loads, four
+//            in flight, candidates pre-filtered by the bound); the lists of a warp are merged once, the 8 warp lists and the seed
+//            list once more.
+// The bounding boxes of consecutive Morton ranges overlap (a range that straddles a high-order boundary of the curve is
+// large), so a query's ball reaches ~30 level-2 nodes but only a few leaves in each: scanning node by node (rounds 1-2) spent
+// a 32-leaf scan and a K-round merge on every one of them, 125 k warp instructions per query.  Pairs are ordered
+// lexicographically (ties towards the lower index, like the brute-force scan of cls3d.cu) and distances use that kernel's
+// expression, so both routes return the same bits.
 __device__ __forceinline__ float point_box_dist2(const float qx, const float qy, const float qz, const Box& b) {
     const float gx = fmaxf(0.f, fmaxf(b.lo.x - qx, qx - b.hi.x));
     const float gy = fmaxf(0.f, fmaxf(b.lo.y - qy, qy - b.hi.y));
@@ -290,163 +301,13 @@ __device__ __forceinline__ void pair_insert(float (&bd)[K], int (&bi)[K], const 
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P, const float4* __restrict__ spts,
-                                                                          const Box* __restrict__ l1, int n1,
-                                                                          const Box* __restrict__ l2, int n2,
-                                                                          const Box* __restrict__ l3, int n3, int S,
-                                                                          const float* __restrict__ points,
-                                                                          const int* __restrict__ sample_idx,
-                                                                          float* __restrict__ cand_d, int* __restrict__ cand_i) {
-    // ONE CTA PER QUERY: its 8 warps share the level-2 nodes (node i2 belongs to warp i2 % 8).  A query's walk is a chain of
-    // dependent loads (boxes -> leaves -> points) through the ~10-50 level-2 nodes that reach its neighbourhood; with one warp
-    // per query the kernel's duration was that chain (0.4 ms for 800 queries: too few warps to hide it behind each other).
-    __shared__ float s_md[kQueryWarps][K];
-    __shared__ int s_mi[kQueryWarps][K];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x;
-    if (s >= S) return;
-    const int si = sample_idx[s];
-    const float qx = points[3 * (size_t)si], qy = points[3 * (size_t)si + 1], qz = points[3 * (size_t)si + 2];
-    float bd[K];  // the K best so far, replicated in every lane
-    int bi[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        bd[j] = FLT_MAX;
-        bi[j] = INT_MAX;
-    }
-    // merge per-lane sorted candidate lists (ld, li) into the replicated list: K rounds of a lexicographic warp minimum over
-    // the lists' heads; a round's winner is inserted if it beats the current K-th, else nothing better is left anywhere
-    auto merge_lane_lists = [&](float (&ld)[K], int (&li)[K]) {
-#pragma unroll
-        for (int r = 0; r < K; ++r) {
-            float hd = ld[0];
-            int hi = li[0];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float od = __shfl_xor_sync(kFull, hd, o);
-                const int oi = __shfl_xor_sync(kFull, hi, o);
-                if (pair_less(od, oi, hd, hi)) {
-                    hd = od;
-                    hi = oi;
-                }
-            }
-            if (!pair_less(hd, hi, bd[K - 1], bi[K - 1])) break;  // warp-uniform
-            pair_insert<K>(bd, bi, hd, hi);
-            if (hi == li[0] && hd == ld[0]) {  // this lane's head won: pop it (point ids are unique)
-#pragma unroll
-                for (int j = 0; j + 1 < K; ++j) {
-                    ld[j] = ld[j + 1];
-                    li[j] = li[j + 1];
-                }
-                ld[K - 1] = FLT_MAX;
-                li[K - 1] = INT_MAX;
-            }
-        }
-    };
-    // one LEAF PER LANE: every lane with `mine` walks the 32 points of its own leaf (independent 16-B loads, issued four at a
-    // time) into a private K-list, pre-filtered by the replicated K-th distance; then the 32 lists are merged.  All surviving
-    // leaves of a level-2 node are scanned at once instead of one after the other with one point per lane, which made a query
-    // a chain of ~100 dependent global loads (0.46 ms for 800 queries of 500 k points: as slow as scanning every point).
-    auto scan_leaves = [&](const bool mine, const int leaf) {
-        float ld[K];
-        int li[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            ld[j] = FLT_MAX;
-            li[j] = INT_MAX;
-        }
-        if (mine) {
-            const int base = leaf * kFan;
-            const int cnt = min(kFan, P - base);
-            const float kth = bd[K - 1];
-            const int kth_i = bi[K - 1];
-            for (int k0 = 0; k0 < cnt; k0 += 4) {
-                float4 c[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) c[u] = (k0 + u < cnt) ? __ldg(spts + base + k0 + u) : make_float4(3e18f, 3e18f, 3e18f, 0.f);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float dx = c[u].x - qx, dy = c[u].y - qy, dz = c[u].z - qz;
-                    const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                    const int id = (int)__float_as_uint(c[u].w);
-                    if (k0 + u < cnt && pair_less(d, id, kth, kth_i) && pair_less(d, id, ld[K - 1], li[K - 1]))
-                        pair_insert<K>(ld, li, d, id);
-                }
-            }
-        }
-        merge_lane_lists(ld, li);
-    };
-    // index of the child (of `count` boxes starting at `first`) nearest to the query: lane-parallel, lowest index on ties
-    auto nearest_child = [&](const Box* __restrict__ boxes, const int first, const int count) -> int {
-        float best = FLT_MAX;
-        int arg = first;
-        for (int c0 = 0; c0 < count; c0 += 32) {
-            const int i = c0 + lane;
-            const float d = i < count ? point_box_dist2(qx, qy, qz, boxes[first + i]) : FLT_MAX;
-            if (d < best) {
-                best = d;
-                arg = first + i;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(kFull, best, o);
-            const int oa = __shfl_xor_sync(kFull, arg, o);
-            if (od < best || (od == best && oa < arg)) {
-                best = od;
-                arg = oa;
-            }
-        }
-        return arg;
-    };
-    // seed the bound: the level-2 node nearest to the query, all of its leaves at once
-    const int s3 = nearest_child(l3, 0, n3);
-    const int seed2 = nearest_child(l2, s3 * kFan, min(kFan, n2 - s3 * kFan));
-    {
-        const int leaf = seed2 * kFan + lane;
-        scan_leaves(leaf < n1, leaf);
-    }
-    // every warp has scanned the seed node and holds the same K pairs; from here on warp w adds the candidates of ITS level-2
-    // nodes.  The union of the eight lists contains the true K nearest; the seed pairs appear in all of them and are dropped
-    // as duplicates in the final merge (point ids are unique, so equal pairs are the same point).
-    const float kSlack = 1.0f - 1e-5f;
-    for (int c3 = 0; c3 < n3; c3 += 32) {
-        const int i3 = c3 + lane;
-        unsigned m3 = __ballot_sync(kFull, i3 < n3 && !(point_box_dist2(qx, qy, qz, l3[i3 < n3 ? i3 : 0]) * kSlack > bd[K - 1]));
-        while (m3) {
-            const int b3 = c3 + __ffs(m3) - 1;
-            m3 &= m3 - 1;
-            const int i2 = b3 * kFan + lane;
-            unsigned m2 = __ballot_sync(kFull, i2 < n2 && i2 != seed2 && (i2 % kQueryWarps) == warp &&
-                                                   !(point_box_dist2(qx, qy, qz, l2[i2 < n2 ? i2 : 0]) * kSlack > bd[K - 1]));
-            while (m2) {
-                const int b2 = b3 * kFan + __ffs(m2) - 1;
-                m2 &= m2 - 1;
-                if (point_box_dist2(qx, qy, qz, l2[b2]) * kSlack > bd[K - 1]) continue;  // the bound tightened meanwhile
-                const int leaf = b2 * kFan + lane;
-                const bool mine = leaf < n1 && !(point_box_dist2(qx, qy, qz, l1[leaf < n1 ? leaf : 0]) * kSlack > bd[K - 1]);
-                if (__any_sync(kFull, mine)) scan_leaves(mine, leaf);
-            }
-        }
-    }
-    // warps -> block: lanes 0..7 of warp 0 take one warp's list each; K rounds of the lexicographic minimum over the heads, every
-    // lane whose head IS the winner pops it (which also removes the duplicates of the seed pairs)
-#pragma unroll
-    for (int j = 0; j < K; ++j)
-        if (lane == j) {
-            s_md[warp][j] = bd[j];
-            s_mi[warp][j] = bi[j];
-        }
-    __syncthreads();
-    if (warp != 0) return;
-    float ld[K];
-    int li[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-        ld[j] = lane < kQueryWarps ? s_md[lane][j] : FLT_MAX;
-        li[j] = lane < kQueryWarps ? s_mi[lane][j] : INT_MAX;
-    }
+// the K smallest pairs of the lanes' sorted lists (ld, li), in order, to `out_d / out_i` (lane 0 writes): K rounds of a
+// lexicographic warp minimum over the lists' heads; every lane whose head IS the winner pops it (equal pairs are the same
+// point, so this also drops duplicates)
+template <int K, typename OutD, typename OutI>
+__device__ __forceinline__ void merge_lists_to(float (&ld)[K], int (&li)[K], OutD out_d, OutI out_i) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int r = 0; r < K; ++r) {
         float hd = ld[0];
@@ -470,10 +331,123 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
             li[K - 1] = INT_MAX;
         }
         if (lane == 0) {
-            cand_d[(size_t)s * K + r] = hd;
-            cand_i[(size_t)s * K + r] = hi;
+            out_d[r] = hd;
+            out_i[r] = hi;
         }
     }
+}
+
+constexpr int kLeafQueue = 1024;  // queued leaves per query; a warp that finds the queue full scans its leaves at once
+
+template <int K>
+__global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P, const float4* __restrict__ spts,
+                                                                          const Box* __restrict__ l1, int n1,
+                                                                          const Box* __restrict__ l2, int n2,
+                                                                          const Box* __restrict__ l3, int n3, int S,
+                                                                          const float* __restrict__ points,
+                                                                          const uint32_t* __restrict__ rank,
+                                                                          const int* __restrict__ sample_idx,
+                                                                          float* __restrict__ cand_d, int* __restrict__ cand_i) {
+    __shared__ float s_md[kQueryWarps + 1][K];  // row kQueryWarps: the seed list
+    __shared__ int s_mi[kQueryWarps + 1][K];
+    __shared__ int s_queue[kLeafQueue];
+    __shared__ int s_qn, s_qvalid, s_seed2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x;
+    if (s >= S) return;
+    const int si = sample_idx[s];
+    const float qx = points[3 * (size_t)si], qy = points[3 * (size_t)si + 1], qz = points[3 * (size_t)si + 2];
+    float ld[K];  // this lane's private candidates
+    int li[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ld[j] = FLT_MAX;
+        li[j] = INT_MAX;
+    }
+    float bound_d = FLT_MAX;  // candidates must beat (bound_d, bound_i): nothing during the seed scan, the seed's K-th afterwards
+    int bound_i = INT_MAX;
+    // this lane walks the 32 points of ITS leaf (independent 16-B loads, four at a time) into its private list
+    auto scan_leaf = [&](const int leaf) {
+        const int base = leaf * kFan;
+        const int cnt = min(kFan, P - base);
+        for (int k0 = 0; k0 < cnt; k0 += 4) {
+            float4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = (k0 + u < cnt) ? __ldg(spts + base + k0 + u) : make_float4(3e18f, 3e18f, 3e18f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float dx = c[u].x - qx, dy = c[u].y - qy, dz = c[u].z - qz;
+                const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                const int id = (int)__float_as_uint(c[u].w);
+                if (k0 + u < cnt && pair_less(d, id, bound_d, bound_i) && pair_less(d, id, ld[K - 1], li[K - 1]))
+                    pair_insert<K>(ld, li, d, id);
+            }
+        }
+    };
+    // ---- seed (warp 0) ----
+    if (warp == 0) {
+        // the level-2 node of the query's own position in the Morton order: its 1024 neighbours along the curve hold most of
+        // the true neighbours (the box NEAREST to the query is useless as a seed: the boxes overlap, many contain it)
+        const int seed2 = (int)(rank[si] / (uint32_t)(kFan * kFan));
+        const int leaf = seed2 * kFan + lane;
+        if (leaf < n1) scan_leaf(leaf);
+        merge_lists_to<K>(ld, li, s_md[kQueryWarps], s_mi[kQueryWarps]);
+        if (lane == 0) {
+            s_seed2 = seed2;
+            s_qn = 0;
+            s_qvalid = kLeafQueue;
+        }
+        // merge_lists_to consumed the lists' heads; start over for the scan phase
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            ld[j] = FLT_MAX;
+            li[j] = INT_MAX;
+        }
+    }
+    __syncthreads();
+    bound_d = s_md[kQueryWarps][K - 1];
+    bound_i = s_mi[kQueryWarps][K - 1];
+    const int seed2 = s_seed2;
+    // ---- collect: surviving leaves of every level-2 node but the seed's ----
+    const float kSlack = 1.0f - 1e-5f;
+    for (int i3 = warp; i3 < n3; i3 += kQueryWarps) {
+        if (point_box_dist2(qx, qy, qz, l3[i3]) * kSlack > bound_d) continue;  // warp-uniform
+        const int i2 = i3 * kFan + lane;
+        unsigned m2 = __ballot_sync(kFull, i2 < n2 && i2 != seed2 && !(point_box_dist2(qx, qy, qz, l2[i2 < n2 ? i2 : 0]) * kSlack > bound_d));
+        while (m2) {
+            const int b2 = i3 * kFan + __ffs(m2) - 1;
+            m2 &= m2 - 1;
+            const int leaf = b2 * kFan + lane;
+            const bool mine = leaf < n1 && !(point_box_dist2(qx, qy, qz, l1[leaf < n1 ? leaf : 0]) * kSlack > bound_d);
+            const unsigned mm = __ballot_sync(kFull, mine);
+            if (mm == 0u) continue;
+            const int cnt = __popc(mm);
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&s_qn, cnt);
+            pos = __shfl_sync(kFull, pos, 0);
+            if (pos + cnt <= kLeafQueue) {
+                if (mine) s_queue[pos + __popc(mm & ((1u << lane) - 1u))] = leaf;
+            } else {  // queue full (degenerate data: many points at the bound): entries from `pos` on are invalid, scan now
+                if (lane == 0) atomicMin(&s_qvalid, pos);
+                if (mine) scan_leaf(leaf);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- scan the queue, one leaf per lane ----
+    const int Q = min(s_qn, s_qvalid);
+    for (int q0 = warp * 32; q0 < Q; q0 += kQueryWarps * 32)
+        if (q0 + lane < Q) scan_leaf(s_queue[q0 + lane]);
+    merge_lists_to<K>(ld, li, s_md[warp], s_mi[warp]);
+    __syncthreads();
+    if (warp != 0) return;
+    // ---- the warps' lists and the seed list -> the query's K nearest ----
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        ld[j] = lane <= kQueryWarps ? s_md[lane][j] : FLT_MAX;
+        li[j] = lane <= kQueryWarps ? s_mi[lane][j] : INT_MAX;
+    }
+    merge_lists_to<K>(ld, li, cand_d + (size_t)s * K, cand_i + (size_t)s * K);
 }
 
 struct KnnScratch {
@@ -483,6 +457,7 @@ struct KnnScratch {
     uint32_t* order[2];
     void* sort_temp;
     float4* spts;
+    uint32_t* rank;
     Box *l1, *l2, *l3;
     int n1, n2, n3, nb_bounds;
     size_t bytes;
@@ -509,6 +484,7 @@ KnnScratch carve_knn(char* base, int P) {
     s.order[1] = (uint32_t*)take((size_t)P * 4);
     s.sort_temp = take(radix_sort_temp_bytes(P));
     s.spts = (float4*)take((size_t)P * sizeof(float4));
+    s.rank = (uint32_t*)take((size_t)P * 4);
     s.l1 = (Box*)take((size_t)s.n1 * sizeof(Box));
     s.l2 = (Box*)take((size_t)s.n2 * sizeof(Box));
     s.l3 = (Box*)take((size_t)s.n3 * sizeof(Box));
@@ -521,7 +497,7 @@ KnnScratch carve_knn(char* base, int P) {
 size_t knn_temp_bytes(int P) { return carve_knn(nullptr, P > 0 ? P : 1).bytes; }
 
 // Morton order + float4 stream + 3-level box hierarchy of `points` into `temp` (knn_temp_bytes(P) bytes)
-int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream) {
+int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream, bool with_rank) {
     if (P <= 0) return 0;
     KnnScratch s = carve_knn(static_cast<char*>(temp), P);
     bounds_partial_kernel<<<s.nb_bounds, 256, 0, stream>>>(P, points, s.bounds_part);
@@ -533,7 +509,7 @@ int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream) 
     int res = 0;
     int rc = radix_sort_pairs_u32(s.codes, s.order, P, 0, 30, /*identity_vals=*/true, s.sort_temp, &res, stream, false);
     if (rc) return rc;
-    gather_points_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, points, s.order[res], s.spts);
+    gather_points_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, points, s.order[res], s.spts, with_rank ? s.rank : nullptr);
     LSX_KERNEL_OK(stream, false);
     build_boxes_kernel<<<ceil_div(s.n1 * 32, 256), 256, 0, stream>>>(P, s.spts, nullptr, s.l1, s.n1);
     LSX_KERNEL_OK(stream, false);
@@ -546,7 +522,7 @@ int knn_tree_build(int P, const float* points, void* temp, cudaStream_t stream) 
 
 int knn_mean_dist2(int P, const float* points, float* out, void* temp, cudaStream_t stream) {
     if (P <= 0) return 0;
-    const int rc = knn_tree_build(P, points, temp, stream);
+    const int rc = knn_tree_build(P, points, temp, stream, /*with_rank=*/false);
     if (rc) return rc;
     KnnScratch s = carve_knn(static_cast<char*>(temp), P);
     knn_query_kernel<<<ceil_div(s.n1, kQueryWarps), kQueryWarps * 32, 0, stream>>>(P, s.spts, s.l1, s.n1, s.l2, s.n2, s.l3,
@@ -566,7 +542,7 @@ int knn_tree_query(int K, int P, const void* tree, int S, const float* points, c
 #define LSX_KNN_CASE(KK)                                                                                                       \
     case KK:                                                                                                                   \
         knn_tree_query_kernel<KK><<<blocks, kQueryWarps * 32, 0, stream>>>(P, s.spts, s.l1, s.n1, s.l2, s.n2, s.l3, s.n3, S,   \
-                                                                           points, sample_idx, cand_d, cand_i);                \
+                                                                           points, s.rank, sample_idx, cand_d, cand_i);        \
         break;
         LSX_KNN_CASE(1)
         LSX_KNN_CASE(2)
