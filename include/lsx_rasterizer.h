@@ -73,7 +73,8 @@ typedef struct lsx_forward_args {
     const float* language_feature_instance;  /* P*Fi (include_feature) */
     const float* opacities;                  /* P */
     const float* scales;                     /* P*3 or NULL */
-    const float* rotations;                  /* P*4 or NULL */
+    const float* rotations;                  /* P*4 or NULL; 16-byte aligned (every other array: 4-byte aligned is enough,
+                                              * rows that happen to be 16-byte aligned are moved with 16-byte accesses) */
     const float* cov3D_precomp;              /* P*6 or NULL */
     const float* all_map;                    /* P*5 (render_geo) */
     const float* viewmatrix;                 /* 16 */

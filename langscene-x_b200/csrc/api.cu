@@ -354,6 +354,10 @@ int lsx_rasterize_forward(const lsx_forward_args* a, int32_t* num_rendered) {
         set_error("lsx_rasterize_forward: raw_params needs scales + rotations and takes neither cov3D_precomp nor all_map");
         return -1;
     }
+    if (reinterpret_cast<uintptr_t>(a->rotations) & 15u) {
+        set_error("lsx_rasterize_forward: rotations must be 16-byte aligned (read as one 16-B word per Gaussian)");
+        return -1;
+    }
     if (!a->colors_precomp && a->M < (a->D + 1) * (a->D + 1)) {
         set_error("lsx_rasterize_forward: sh has %d coefficients but degree %d needs %d", a->M, a->D,
                   (a->D + 1) * (a->D + 1));
@@ -625,6 +629,10 @@ int lsx_rasterize_backward(const lsx_backward_args* a) {
     bp.pose_partials = gm.pose_partials; bp.dL_dpose = a->dL_dpose; bp.accumulate_pose = a->accumulate_pose;
     if (a->raw_params && (a->cov3D_precomp || !a->scales || !a->rotations)) {
         set_error("lsx_rasterize_backward: raw_params needs scales + rotations and no cov3D_precomp");
+        return -1;
+    }
+    if ((reinterpret_cast<uintptr_t>(a->rotations) | reinterpret_cast<uintptr_t>(a->dL_drotations)) & 15u) {
+        set_error("lsx_rasterize_backward: rotations and dL_drotations must be 16-byte aligned");
         return -1;
     }
     bp.geo_scale_x = 0.5f * (float)W; bp.geo_scale_y = 0.5f * (float)H;

@@ -94,6 +94,10 @@ extern "C" int lsx_gaussian_head_forward(int32_t P, const float* viewmatrix, con
         return -1;
     }
     if (P == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(rotations)) & 15u) {
+        set_error("lsx_gaussian_head_forward: the (P, 4) rotation arrays must be 16-byte aligned");
+        return -1;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     gaussian_head_fwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw,
                                                                    opacity_raw, scales, rotations, opacity, all_map);
@@ -114,6 +118,11 @@ extern "C" int lsx_gaussian_head_backward_acc(int32_t P, const float* viewmatrix
         return -1;
     }
     if (P == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(dL_drotations) |
+         reinterpret_cast<uintptr_t>(dL_drotation_raw)) & 15u) {
+        set_error("lsx_gaussian_head_backward: the (P, 4) rotation arrays must be 16-byte aligned");
+        return -1;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     gaussian_head_bwd_kernel<<<ceil_div(P, 256), 256, 0, stream>>>(P, viewmatrix, campos, xyz, scaling_raw, rotation_raw,
                                                                    opacity_raw, dL_dscales, dL_drotations,

@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
     const int s = blockIdx.x;
     if (s >= S) return;
     const int si = sample_idx[s];
+    LSX_CHECK_INDEX(si, P, "sampled point index");
     const float qx = points[3 * (size_t)si], qy = points[3 * (size_t)si + 1], qz = points[3 * (size_t)si + 2];
     float ld[K];  // this lane's private candidates
     int li[K];
@@ -368,6 +369,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
     int bound_i = INT_MAX;
     // this lane walks the 32 points of ITS leaf (independent 16-B loads, four at a time) into its private list
     auto scan_leaf = [&](const int leaf) {
+        LSX_CHECK_INDEX(leaf, n1, "leaf of the box hierarchy");
         const int base = leaf * kFan;
         const int cnt = min(kFan, P - base);
         for (int k0 = 0; k0 < cnt; k0 += 4) {
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
     if (warp == 0) {
         // the level-2 node of the query's own position in the Morton order: its 1024 neighbours along the curve hold most of
         // the true neighbours (the box NEAREST to the query is useless as a seed: the boxes overlap, many contain it)
+        LSX_CHECK_INDEX(rank[si], P, "rank of the query in the Morton order");
         const int seed2 = (int)(rank[si] / (uint32_t)(kFan * kFan));
         const int leaf = seed2 * kFan + lane;
         if (leaf < n1) scan_leaf(leaf);
@@ -426,7 +429,10 @@ __global__ void __launch_bounds__(kQueryWarps * 32) knn_tree_query_kernel(int P,
             if (lane == 0) pos = atomicAdd(&s_qn, cnt);
             pos = __shfl_sync(kFull, pos, 0);
             if (pos + cnt <= kLeafQueue) {
-                if (mine) s_queue[pos + __popc(mm & ((1u << lane) - 1u))] = leaf;
+                if (mine) {
+                    LSX_CHECK_INDEX(pos + __popc(mm & ((1u << lane) - 1u)), kLeafQueue, "leaf queue slot");
+                    s_queue[pos + __popc(mm & ((1u << lane) - 1u))] = leaf;
+                }
             } else {  // queue full (degenerate data: many points at the bound): entries from `pos` on are invalid, scan now
                 if (lane == 0) atomicMin(&s_qvalid, pos);
                 if (mine) scan_leaf(leaf);

@@ -192,6 +192,10 @@ extern "C" int lsx_pose_transform_forward(int32_t P, const float* pose, const fl
         return -1;
     }
     if (P == 0) return 0;
+    if ((reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(out_rotations)) & 15u) {
+        set_error("lsx_pose_transform_forward: the (P, 4) rotation arrays must be 16-byte aligned");
+        return -1;
+    }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int blocks = (P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8;
     pose_fwd_kernel<<<blocks, 256, 0, stream>>>(P, pose, xyz, rotation_raw, out_means3D, out_rotations);
@@ -204,6 +208,11 @@ extern "C" int lsx_pose_transform_backward(int32_t P, const float* pose, const f
                                            float* dL_drotation_raw, float* dL_dpose, float* partials, void* stream_) {
     if (P < 0 || !pose || !dL_dpose || !partials || (P > 0 && (!xyz || !dL_dxyz || (dL_drotations && !rotation_raw)))) {
         set_error("lsx_pose_transform_backward: bad arguments");
+        return -1;
+    }
+    if ((reinterpret_cast<uintptr_t>(rotation_raw) | reinterpret_cast<uintptr_t>(dL_drotations) |
+         reinterpret_cast<uintptr_t>(dL_drotation_raw)) & 15u) {
+        set_error("lsx_pose_transform_backward: the (P, 4) rotation arrays must be 16-byte aligned");
         return -1;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

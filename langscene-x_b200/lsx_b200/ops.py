@@ -38,6 +38,14 @@ def _prep(t, name, device):
     return t.contiguous()
 
 
+def _aligned16(t):
+    """The kernels read `rotations` as one 16-B word per Gaussian (and write its gradient the same way): a contiguous tensor
+    that starts at an odd float of its storage is copied to a fresh allocation (the C ABI rejects it, include/lsx_rasterizer.h)."""
+    if t is not None and t.numel() and t.data_ptr() % 16:
+        return t.clone()
+    return t
+
+
 class _ScratchAlloc:
     """The resizeFunctional analogue (rasterize_points.cu:27-33): torch owns the scratch bytes.
 
@@ -139,7 +147,7 @@ def rasterize_gaussians(
     language_feature_instance = _prep(language_feature_instance, "language_feature_instance_precomp", device)
     opacity = _prep(opacity, "opacities", device)
     scales = _prep(scales, "scales", device)
-    rotations = _prep(rotations, "rotations", device)
+    rotations = _aligned16(_prep(rotations, "rotations", device))
     cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
     all_map = _prep(all_map, "all_map", device)
     viewmatrix = _prep(viewmatrix, "viewmatrix", device)
@@ -262,7 +270,7 @@ def rasterize_gaussians_backward(
     colors = _prep(colors, "colors_precomp", device)
     all_maps = _prep(all_maps, "all_map", device)
     scales = _prep(scales, "scales", device)
-    rotations = _prep(rotations, "rotations", device)
+    rotations = _aligned16(_prep(rotations, "rotations", device))
     cov3D_precomp = _prep(cov3D_precomp, "cov3D_precomp", device)
     viewmatrix = _prep(viewmatrix, "viewmatrix", device)
     projmatrix = _prep(projmatrix, "projmatrix", device)

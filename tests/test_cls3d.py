@@ -123,15 +123,19 @@ def test_cuda_errors():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N,C,k,S,dup", [(500_000, 3, 5, 800, False), (70_000, 16, 8, 300, False), (1500, 3, 5, 64, True),
-                                         (20, 2, 3, 20, False), (33, 1, 1, 7, True)])
+                                         (20, 2, 3, 20, False), (33, 1, 1, 7, True), (40_000, 3, 5, 24, "all"),
+                                         (2_000_000, 3, 5, 100, False)])
 def test_tree_search_returns_the_brute_force_neighbours(N, C, k, S, dup):
     """loss_cls_3d(..., tree=knn_tree(xyz)): the neighbour search through the Morton / box hierarchy must return exactly what the
     scan of all points returns — same indices in the same order (ties towards the lower index: `dup` plants coincident points),
-    hence the same loss and gradient bits — at sizes with one, two and three populated hierarchy levels."""
+    hence the same loss and gradient bits — at sizes with one, two and three populated hierarchy levels, and on degenerate data
+    (all points coincident) where nothing can be pruned."""
     from lsx_b200.loss import knn_tree, loss_cls_3d
     g = torch.Generator().manual_seed(N + k)
     xyz = (torch.rand(N, 3, generator=g) * 6 - 3)
-    if dup:
+    if dup == "all":
+        xyz[:] = xyz[0].clone()     # every point coincides: all 1250 leaves tie with the bound, the leaf queue (1024) overflows
+    elif dup:
         xyz[N // 2:] = xyz[:N - N // 2].clone()                      # every point of the second half coincides with one of the first
     xyz = xyz.cuda()
     pred = torch.randn(N, C, generator=g).cuda()
@@ -144,6 +148,11 @@ def test_tree_search_returns_the_brute_force_neighbours(N, C, k, S, dup):
         loss.backward()
         out[name] = (loss.detach(), nbr, p.grad)
     assert torch.equal(out["scan"][1], out["tree"][1])
-    assert torch.equal(out["scan"][0], out["tree"][0]) and torch.equal(out["scan"][2], out["tree"][2])
+    assert torch.equal(out["scan"][0], out["tree"][0])
+    if dup == "all":   # every sample shares the same k neighbour rows: the backward's atomics onto them reorder between runs
+        scale = float(out["scan"][2].abs().max())
+        assert float((out["scan"][2] - out["tree"][2]).abs().max()) <= 1e-5 * scale
+    else:
+        assert torch.equal(out["scan"][2], out["tree"][2])
     with pytest.raises(RuntimeError, match="another point count"):
         loss_cls_3d(xyz[:-1].contiguous(), pred[:-1].contiguous(), k, 2.0, 10_000_000, S, sample_indices=samples % (N - 1), tree=tree)
