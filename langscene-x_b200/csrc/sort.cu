@@ -122,23 +122,26 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __
 // launches) over the digit-major table.  No inter-block waiting anywhere.
 constexpr int kGroup = 64;
 
+// IT = keys per thread (a block sorts 256 IT keys): 16 for long arrays; 8 / 4 for short ones, whose few blocks are bound by the
+// latency of one block's serial ranking work, not by throughput (radix_items below).
+template <int IT>
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __restrict__ keys, int n, int shift,
                                                               uint32_t mask, uint32_t* __restrict__ hist,
                                                               uint32_t* __restrict__ gsum) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kTile;
-    // all 16 keys of the thread are fetched before the first shared-memory atomic (interleaved, every atomic waited for
+    const int base = blockIdx.x * (kThreads * IT);
+    // all keys of the thread are fetched before the first shared-memory atomic (interleaved, every atomic waited for
     // its own load: the kernel was a chain of 16 exposed global-load latencies)
-    uint32_t k[kItems];
+    uint32_t k[IT];
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = base + i * kThreads + threadIdx.x;
         k[i] = idx < n ? __ldg(keys + idx) : 0u;
     }
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = base + i * kThreads + threadIdx.x;
         if (idx < n) atomicAdd(&h[(k[i] >> shift) & mask], 1u);
     }
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
 }
 
 // 3 CTAs / SM (80 registers): measured 0.169 -> 0.151 ms for the two tile passes at C3 against 2 CTAs / SM; 4 spills
+template <int IT>
 __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ keys_out,
@@ -160,7 +164,9 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
                                                                  const uint32_t* __restrict__ gsum) {
     __shared__ uint32_t cnt[kWarps][256];
     __shared__ uint32_t s_warp[32];
-    __shared__ __align__(16) uint32_t s_key[kTile], s_val[kTile];   // the block's pairs regrouped by digit before they leave
+    constexpr int TILE = kThreads * IT;
+    static_assert(TILE >= 1024, "the offset step reuses the first 1024 words of s_key");
+    __shared__ __align__(16) uint32_t s_key[TILE], s_val[TILE];   // the block's pairs regrouped by digit before they leave
     __shared__ uint32_t s_lstart[256], s_gbase[256];  // per digit: start inside the block / in the output array
     uint32_t my_start;  // global position of this block's first key with digit threadIdx.x
     {
@@ -189,30 +195,31 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wbase = blockIdx.x * kTile + warp * (32 * kItems);
+    const int wbase = blockIdx.x * TILE + warp * (32 * IT);
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     // keys AND values are fetched up front, 32 independent loads per thread in flight (fetching a value only when it
     // is regrouped exposes one global-load latency per item: 40 % of this kernel's stall samples before the change)
-    uint32_t key[kItems], val[kItems];
-    uint32_t rank[kItems / 2];  // two 16-bit ranks per register (a warp segment holds 512 keys)
+    uint32_t key[IT], val[IT];
+    uint32_t rank[IT / 2];  // two 16-bit ranks per register (a warp segment holds 512 keys)
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = wbase + i * 32 + lane;
         key[i] = idx < n ? keys_in[idx] : 0u;
     }
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = wbase + i * 32 + lane;
         val[i] = (vals_in && idx < n) ? vals_in[idx] : (uint32_t)idx;
     }
     // ranking in groups of 8 items: the warp matches of a group are independent and issue back to back; only the
     // counter updates (leader lane per distinct digit) form a serial chain
+    constexpr int G = IT < 8 ? IT : 8;
 #pragma unroll
-    for (int g = 0; g < kItems; g += 8) {
-        uint32_t peers[8];
+    for (int g = 0; g < IT; g += G) {
+        uint32_t peers[G];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < G; ++j) {
             const int idx = wbase + (g + j) * 32 + lane;
             // lanes with the same digit, from 8 ballots (one per digit bit) instead of MATCH.ANY, whose result the warp waits
             // for (half of this kernel's stall samples with it; C3 tile sort 0.151 -> 0.128 ms, C5 0.69 -> 0.59); digit bits
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
             peers[j] = pm;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < G; ++j) {
             const int idx = wbase + (g + j) * 32 + lane;
             const bool valid = idx < n;
             const uint32_t d = (key[g + j] >> shift) & mask;
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
     __syncthreads();
     // local shuffle: the block's keys (and values) land in shared memory grouped by digit, in stable order
 #pragma unroll
-    for (int i = 0; i < kItems; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int idx = wbase + i * 32 + lane;
         if (idx < n) {
             const uint32_t d = (key[i] >> shift) & mask;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32
     }
     __syncthreads();
     // write out: consecutive threads write consecutive positions of a digit's run (coalesced within runs)
-    const int count = min(kTile, n - (int)blockIdx.x * kTile);
+    const int count = min(TILE, n - (int)blockIdx.x * TILE);
     for (int j = threadIdx.x; j < count; j += kThreads) {
         const uint32_t k = s_key[j];
         const uint32_t d = (k >> shift) & mask;
@@ -314,8 +321,15 @@ constexpr int kMaxPasses = 4;  // 32-bit keys, 8-bit digits
 
 static size_t gsum_words(int nb) { return (size_t)256 * (1 + ceil_div(nb, kGroup)); }
 
+// keys per thread for an array of n keys: a short array gets smaller blocks, so that its sort is not one partial wave of blocks
+// that each rank 16 keys per thread one after the other (444 blocks are resident at 3 per SM).  Depth sort: C1 (10 k keys)
+// 0.063 -> 0.042 ms, C2 (100 k) 0.070 -> 0.055, C4 (500 k) 0.072 -> 0.063 (profiles/r7a_stage_times.jsonl); what is left is
+// launch latency: 8 kernels of ~5-8 us (4 keys per thread at 500 k changes nothing)
+static int radix_items(int n) { return n <= 300 * 1024 ? 4 : (n <= 880 * 1024 ? 8 : 16); }
+
+// sized for the smallest block whatever n is, so that the size stays monotonic in n (lsx_binning_capacity inverts it)
 size_t radix_sort_temp_bytes(int n) {
-    const int nb = ceil_div(n > 0 ? n : 1, kTile);
+    const int nb = ceil_div(n > 0 ? n : 1, kThreads * 4);
     return align_up((size_t)256 * nb * sizeof(uint32_t), 256) + kMaxPasses * gsum_words(nb) * sizeof(uint32_t);
 }
 
@@ -327,7 +341,8 @@ int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_
         set_error("radix_sort_pairs_u32: more than %d passes requested (bits %d..%d)", kMaxPasses, begin_bit, end_bit);
         return -1;
     }
-    const int nb = ceil_div(n, kTile);
+    const int items = radix_items(n);
+    const int nb = ceil_div(n, kThreads * items);
     uint32_t* hist = static_cast<uint32_t*>(temp);
     uint32_t* gsum_all = reinterpret_cast<uint32_t*>(static_cast<char*>(temp) + align_up((size_t)256 * nb * sizeof(uint32_t), 256));
     const size_t gw = gsum_words(nb);
@@ -339,11 +354,23 @@ int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_
         const int bits = (end_bit - shift) < 8 ? (end_bit - shift) : 8;
         const uint32_t mask = (1u << bits) - 1u;
         uint32_t* gsum = gsum_all + pass * gw;
-        radix_hist_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
-        LSX_KERNEL_OK(stream, debug);
         const uint32_t* vin = (first && identity_vals) ? nullptr : vals[cur];
-        radix_scatter_kernel<<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
-                                                          hist, gsum);
+        if (items == 4) {
+            radix_hist_kernel<4><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            LSX_KERNEL_OK(stream, debug);
+            radix_scatter_kernel<4><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+                                                                 hist, gsum);
+        } else if (items == 8) {
+            radix_hist_kernel<8><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            LSX_KERNEL_OK(stream, debug);
+            radix_scatter_kernel<8><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+                                                                 hist, gsum);
+        } else {
+            radix_hist_kernel<16><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            LSX_KERNEL_OK(stream, debug);
+            radix_scatter_kernel<16><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+                                                                  hist, gsum);
+        }
         LSX_KERNEL_OK(stream, debug);
         cur ^= 1;
         first = false;
