@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
 }
 
 // 3 CTAs / SM (80 registers): measured 0.169 -> 0.151 ms for the two tile passes at C3 against 2 CTAs / SM; 4 spills
-template <int IT>
-__global__ void __launch_bounds__(kThreads, 3) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+// MINB = 3: 80 registers; MINB = 4: 64 registers and 14 spilled words — pays only on long arrays (several waves of blocks):
+// C5's tile sort (26 M pairs) 0.552 -> 0.480 ms, its depth sort (5 M) 0.223 -> 0.216; at 1 M keys it costs 3-5 %
+template <int IT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
                                                                  const uint32_t* __restrict__ vals_in,
                                                                  uint32_t* __restrict__ keys_out,
                                                                  uint32_t* __restrict__ vals_out, int n, int shift,
@@ -358,18 +360,22 @@ int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_
         if (items == 4) {
             radix_hist_kernel<4><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
-            radix_scatter_kernel<4><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+            radix_scatter_kernel<4, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
                                                                  hist, gsum);
         } else if (items == 8) {
             radix_hist_kernel<8><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
-            radix_scatter_kernel<8><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+            radix_scatter_kernel<8, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
                                                                  hist, gsum);
         } else {
             radix_hist_kernel<16><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
-            radix_scatter_kernel<16><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
-                                                                  hist, gsum);
+            if (n >= 3 * 1024 * 1024)
+                radix_scatter_kernel<16, 4><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                                                                         mask, hist, gsum);
+            else
+                radix_scatter_kernel<16, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                                                                         mask, hist, gsum);
         }
         LSX_KERNEL_OK(stream, debug);
         cur ^= 1;
