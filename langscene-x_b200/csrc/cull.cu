@@ -87,8 +87,10 @@ __device__ __forceinline__ unsigned footprint_mask(const float mx, const float m
 // for each of the tile's eight 8x4 blocks, the COMPACTED list of the entries whose bit is set — their positions inside the
 // tile's range, in list (= depth) order — at blk_list[w * list_stride + range.x ...] and its length at blk_cnt[8 tile + w].
 // The render kernels walk these lists (tile_stage.cuh: ListStage): full 16-entry rounds, no per-round mask / ballot work.
-// Ordered compaction per 256-entry chunk: 8 warp ballots give the warp totals (lane w keeps bit w's), a 64-word exchange
-// turns them into per-warp bases (lanes 0..7), a second round of ballots places every set bit.
+// Ordered compaction per 256-entry chunk: the threads leave their mask bytes in shared memory and warp w compacts bit w of
+// all 256 of them (8 ballots): it alone owns block w's list, so no prefix has to be exchanged between warps (the first version
+// let every lane place its own 8 bits — 8 ballots, a 64-word exchange and 8 shuffled bases per lane: 40 % of the kernel's
+// instructions and two thirds of its stall samples, profiles/r6q_ncu_helpers_c5.md).
 __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __restrict__ ranges,
                                                               const uint32_t* __restrict__ point_list,
                                                               const float* __restrict__ records, int rec_stride,
@@ -96,14 +98,15 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
                                                               uint32_t* __restrict__ blk_list, size_t list_stride,
                                                               uint32_t* __restrict__ blk_cnt, int chk_points) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ uint32_t s_cnt[2][8][8];  // [chunk parity][warp][block]: double-buffered, one barrier per chunk
+    __shared__ uint8_t s_m[2][256];  // [chunk parity][entry of the chunk]: double-buffered, one barrier per chunk
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
     const uint32_t n = r.y - r.x;
     const float tx0 = (float)((tile % grid_x) * TILE_X), ty0 = (float)((tile / grid_x) * TILE_Y);
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
-    uint32_t run = 0;  // lanes 0..7 (of every warp): entries of block `lane` emitted by earlier chunks
+    uint32_t run = 0;  // entries of block `warp` emitted by earlier chunks (warp-uniform)
+    uint32_t* my_list = blk_list + (size_t)warp * list_stride + r.x;
     // software pipeline over the 256-entry chunks: the record head of chunk c + 1 and the Gaussian index of chunk c + 2
     // are in flight while chunk c is classified and compacted (the two loads are dependent: index -> record)
     auto load_id = [&](uint32_t i) -> uint32_t {
@@ -139,39 +142,22 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
             m = footprint_mask(h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, tx0, ty0);
             masks[r.x + i] = (uint8_t)m;
         }
-        unsigned bal[8];
-        uint32_t wtotal = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            bal[w] = __ballot_sync(kFull, (m >> w) & 1u);
-            if (lane == (unsigned)w) wtotal = __popc(bal[w]);
-        }
-        if (lane < 8) s_cnt[parity][warp][lane] = wtotal;
+        s_m[parity][threadIdx.x] = (uint8_t)m;
         __syncthreads();
-        uint32_t wbase = 0;
-        if (lane < 8) {
-            uint32_t before = 0, total = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < 8; ++w2) {
-                const uint32_t c = s_cnt[parity][w2][lane];
-                before += ((unsigned)w2 < warp) ? c : 0u;
-                total += c;
+        for (int j = 0; j < 8; ++j) {
+            const bool set = (s_m[parity][j * 32 + lane] >> warp) & 1u;
+            const unsigned bal = __ballot_sync(kFull, set);
+            if (set) {
+                LSX_CHECK_INDEX(run + __popc(bal & lt), n, "block list write");
+                my_list[run + __popc(bal & lt)] = base + (uint32_t)(j * 32) + lane;
             }
-            wbase = run + before;
-            run += total;
-        }
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t b0 = __shfl_sync(kFull, wbase, w);
-            if ((m >> w) & 1u) {
-                LSX_CHECK_INDEX(b0 + __popc(bal[w] & lt), n, "block list write");
-                blk_list[(size_t)w * list_stride + r.x + b0 + __popc(bal[w] & lt)] = i;
-            }
+            run += __popc(bal);
         }
         h0 = nh0;
         h1 = nh1;
     }
-    if (warp == 0 && lane < 8) blk_cnt[8 * tile + lane] = run;
+    if (lane == 0) blk_cnt[8 * tile + warp] = run;
 }
 
 }  // namespace
