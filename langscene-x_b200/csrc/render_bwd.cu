@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
 template <int CT4>
 int launch_bwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
+    // (16 channels: asking for 24 / 28 / 32 CTAs per SM — 80 / 72 / 64 registers — is 5 / 13 / 49 % slower than the 96 registers
+    // ptxas picks on its own, profiles/r7d_bwd16_ab.log)
     constexpr int MB = (CT4 == 28) ? 20 : 0;
     const size_t smem = ListStage<RS>::kSmemBytes;
     const long long blocks = (long long)p.grid_x * p.grid_y * 8;
