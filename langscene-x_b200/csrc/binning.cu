@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) emit_tile_pairs_kernel(int P, const uint3
 // R = number of slots (real pairs followed by 0xffffffff padding keys, which belong to no tile)
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int R, const uint32_t* __restrict__ keys,
                                                           uint2* __restrict__ ranges, const uint32_t num_tiles) {
+    pdl_wait();
     const long long base = 4ll * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
     if (base >= R) return;
     uint32_t k[4];
@@ -144,7 +145,7 @@ int launch_tile_ranges(int R, const uint32_t* sorted_tile_keys, uint2* ranges, i
                        bool debug) {
     LSX_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)num_tiles * sizeof(uint2), stream));
     if (R <= 0) return 0;
-    tile_ranges_kernel<<<ceil_div(ceil_div(R, 4), 256), 256, 0, stream>>>(R, sorted_tile_keys, ranges, (uint32_t)num_tiles);
+    launch_pdl(tile_ranges_kernel, ceil_div(ceil_div(R, 4), 256), 256, 0, stream, R, sorted_tile_keys, ranges, (uint32_t)num_tiles);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

@@ -42,6 +42,43 @@ void count_launch(int n = 1);
         }                                                                                        \
     } while (0)
 
+// ---- programmatic dependent launch (sm_90+) ---------------------------------------------------------------------------
+// A kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still running: its blocks
+// become resident as the predecessor's last wave drains instead of after the grid has been retired (measured on the
+// radix passes: ~1.2 us per kernel boundary, profiles/r8n_pdl.log).  Such a kernel executes pdl_wait() before it touches
+// global memory: it returns once every prerequisite grid has completed and its writes are visible — ordinary stream
+// semantics from there on — and lets the NEXT kernel of the stream be scheduled in the same way.
+#ifndef LSX_PDL
+#define LSX_PDL 1
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+#if LSX_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), long long grid, int block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+#if LSX_PDL
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in LSX_KERNEL_OK
+#else
+    kernel<<<(unsigned)grid, block, smem, stream>>>(static_cast<KArgs>(args)...);
+#endif
+}
+#endif
+
 // ---- LSX_BOUNDS_CHECK build (the pool refuses compute-sanitizer: profiles/r6d_compute_sanitizer_refused.txt) ------
 // -DLSX_BOUNDS_CHECK=1 turns every data-dependent index of the binning / list / record structures into a checked access:
 // an out-of-range index prints its site and traps (the launch then fails and the C ABI returns an error).  The default build

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* _
                                                                const uint32_t* __restrict__ gather, int n,
                                                                uint32_t* __restrict__ partials) {
     __shared__ uint32_t s_warp[32];
+    pdl_wait();
     const int base = blockIdx.x * kTile;
     uint32_t sum = 0;
 #pragma unroll
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(kThreads) scan_reduce_kernel(const uint32_t* _
 __global__ void __launch_bounds__(1024) scan_partials_kernel(uint32_t* __restrict__ partials, int nb,
                                                              uint32_t* __restrict__ total_out) {
     __shared__ uint32_t s_warp[32];
+    pdl_wait();
     uint32_t carry = 0;
     for (int base = 0; base < nb; base += 1024) {
         const int idx = base + threadIdx.x;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(kThreads) scan_apply_kernel(const uint32_t* __
                                                               uint32_t* __restrict__ out, int n,
                                                               const uint32_t* __restrict__ partials) {
     __shared__ uint32_t s_warp[32];
+    pdl_wait();
     const int base = blockIdx.x * kTile + threadIdx.x * kItems;  // blocked arrangement
     uint32_t v[kItems];
     uint32_t sum = 0;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const uint32_t* __
                                                               uint32_t* __restrict__ gsum) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
+    pdl_wait();
     __syncthreads();
     const int base = blockIdx.x * (kThreads * IT);
     // all keys of the thread are fetched before the first shared-memory atomic (interleaved, every atomic waited for
@@ -168,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, MINB) radix_scatter_kernel(const uin
     __shared__ uint32_t s_warp[32];
     constexpr int TILE = kThreads * IT;
     static_assert(TILE >= 1024, "the offset step reuses the first 1024 words of s_key");
+    pdl_wait();
     __shared__ __align__(16) uint32_t s_key[TILE], s_val[TILE];   // the block's pairs regrouped by digit before they leave
     __shared__ uint32_t s_lstart[256], s_gbase[256];  // per digit: start inside the block / in the output array
     uint32_t my_start;  // global position of this block's first key with digit threadIdx.x
@@ -310,11 +315,11 @@ int exclusive_scan_u32(const uint32_t* in, const uint32_t* gather, uint32_t* out
     }
     const int nb = ceil_div(n, kTile);
     uint32_t* partials = static_cast<uint32_t*>(temp);
-    scan_reduce_kernel<<<nb, kThreads, 0, stream>>>(in, gather, n, partials);
+    launch_pdl(scan_reduce_kernel, nb, kThreads, 0, stream, in, gather, n, partials);
     LSX_KERNEL_OK(stream, debug);
-    scan_partials_kernel<<<1, 1024, 0, stream>>>(partials, nb, total);
+    launch_pdl(scan_partials_kernel, 1, 1024, 0, stream, partials, nb, total);
     LSX_KERNEL_OK(stream, debug);
-    scan_apply_kernel<<<nb, kThreads, 0, stream>>>(in, gather, out, n, partials);
+    launch_pdl(scan_apply_kernel, nb, kThreads, 0, stream, in, gather, out, n, partials);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
@@ -358,23 +363,23 @@ int radix_sort_pairs_u32(uint32_t* keys[2], uint32_t* vals[2], int n, int begin_
         uint32_t* gsum = gsum_all + pass * gw;
         const uint32_t* vin = (first && identity_vals) ? nullptr : vals[cur];
         if (items == 4) {
-            radix_hist_kernel<4><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            launch_pdl(radix_hist_kernel<4>, nb, kThreads, 0, stream, keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
-            radix_scatter_kernel<4, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+            launch_pdl(radix_scatter_kernel<4, 3>, nb, kThreads, 0, stream, keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
                                                                  hist, gsum);
         } else if (items == 8) {
-            radix_hist_kernel<8><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            launch_pdl(radix_hist_kernel<8>, nb, kThreads, 0, stream, keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
-            radix_scatter_kernel<8, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
+            launch_pdl(radix_scatter_kernel<8, 3>, nb, kThreads, 0, stream, keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift, mask,
                                                                  hist, gsum);
         } else {
-            radix_hist_kernel<16><<<nb, kThreads, 0, stream>>>(keys[cur], n, shift, mask, hist, gsum);
+            launch_pdl(radix_hist_kernel<16>, nb, kThreads, 0, stream, keys[cur], n, shift, mask, hist, gsum);
             LSX_KERNEL_OK(stream, debug);
             if (n >= 3 * 1024 * 1024)
-                radix_scatter_kernel<16, 4><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                launch_pdl(radix_scatter_kernel<16, 4>, nb, kThreads, 0, stream, keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
                                                                          mask, hist, gsum);
             else
-                radix_scatter_kernel<16, 3><<<nb, kThreads, 0, stream>>>(keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
+                launch_pdl(radix_scatter_kernel<16, 3>, nb, kThreads, 0, stream, keys[cur], vin, keys[cur ^ 1], vals[cur ^ 1], n, shift,
                                                                          mask, hist, gsum);
         }
         LSX_KERNEL_OK(stream, debug);
