@@ -45,9 +45,12 @@ void count_launch(int n = 1);
 // ---- programmatic dependent launch (sm_90+) ---------------------------------------------------------------------------
 // A kernel launched with launch_pdl() may be scheduled while its predecessor in the stream is still running: its blocks
 // become resident as the predecessor's last wave drains instead of after the grid has been retired (measured on the
-// radix passes: ~1.2 us per kernel boundary, profiles/r8n_pdl.log).  Such a kernel executes pdl_wait() before it touches
-// global memory: it returns once every prerequisite grid has completed and its writes are visible — ordinary stream
+// radix passes: ~1.2 us per kernel boundary, profiles/r8n_pdl_radix_only.log).  Such a kernel executes pdl_wait() before it
+// touches global memory: it returns once every prerequisite grid has completed and its writes are visible — ordinary stream
 // semantics from there on — and lets the NEXT kernel of the stream be scheduled in the same way.
+// Used for the chains of SHORT kernels only (radix passes, scans, tile ranges: 14 of a forward call's launches).  On the
+// multi-wave kernels (footprint, forward render, preprocess_bwd behind the backward render) the stage timers improve too,
+// but the real back-to-back step gets 1 % slower at C3 (profiles/r8q_pdl_bench_ab.log, r8r_pdl_bench_ab2.log): removed.
 #ifndef LSX_PDL
 #define LSX_PDL 1
 #endif

@@ -99,7 +99,6 @@ __global__ void __launch_bounds__(256) footprint_masks_kernel(const uint2* __res
                                                               uint32_t* __restrict__ blk_cnt, int chk_points) {
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ uint8_t s_m[2][256];  // [chunk parity][entry of the chunk]: double-buffered, one barrier per chunk
-    pdl_wait();
     const int tile = blockIdx.x;
     const uint2 r = ranges[tile];
     const uint32_t n = r.y - r.x;
@@ -167,8 +166,8 @@ int launch_footprint_masks(int num_tiles, const uint2* ranges, const uint32_t* p
                            int rec_stride, uint32_t grid_x, uint8_t* masks, uint32_t* blk_list, size_t list_stride,
                            uint32_t* blk_cnt, int num_points, cudaStream_t stream, bool debug) {
     if (num_tiles <= 0) return 0;
-    launch_pdl(footprint_masks_kernel, num_tiles, 256, 0, stream, ranges, point_list, records, rec_stride, grid_x, masks, blk_list,
-               list_stride, blk_cnt, num_points);
+    footprint_masks_kernel<<<num_tiles, 256, 0, stream>>>(ranges, point_list, records, rec_stride, grid_x, masks, blk_list,
+                                                         list_stride, blk_cnt, num_points);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }

@@ -833,7 +833,6 @@ __device__ __forceinline__ void row_put(float* __restrict__ dst, const float* __
 // only meets for the pose-gradient partial sums of the fused-wrapper mode.
 template <bool RAW>
 __global__ void __launch_bounds__(kPreBwdThreads, RAW ? LSX_PRE_BWD_MINB_RAW : LSX_PRE_BWD_MINB) preprocess_bwd_kernel(const PreprocessBwdParams p) {
-    pdl_wait();
     const int n_sh = p.M * 3;
     const int idx = blockIdx.x * kPreBwdThreads + threadIdx.x;
     const unsigned am = (unsigned)p.accumulate;
@@ -943,7 +942,7 @@ int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, boo
     const int blocks = ceil_div(p.P, kPreBwdThreads);
     if (p.raw_params) {
         LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel<true>), smem, 3));
-        launch_pdl(preprocess_bwd_kernel<true>, blocks, kPreBwdThreads, smem, stream, p);
+        preprocess_bwd_kernel<true><<<blocks, kPreBwdThreads, smem, stream>>>(p);
         LSX_KERNEL_OK(stream, debug);
         if (p.pose != nullptr && p.dL_dpose != nullptr) {
             const int rc = launch_pose_finish(blocks, p.pose, p.pose_partials, p.dL_dpose, p.accumulate_pose, stream);
@@ -951,7 +950,7 @@ int launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream, boo
         }
     } else {
         LSX_CUDA_OK(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_bwd_kernel<false>), smem, 1));
-        launch_pdl(preprocess_bwd_kernel<false>, blocks, kPreBwdThreads, smem, stream, p);
+        preprocess_bwd_kernel<false><<<blocks, kPreBwdThreads, smem, stream>>>(p);
         LSX_KERNEL_OK(stream, debug);
     }
     return 0;

@@ -130,7 +130,6 @@ __global__ void __launch_bounds__(32, MB) render_bwd_kernel(const RenderParams p
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(16) float s_w[2][(1 + NX) * XROW];  // weights + NX geometry terms, double buffered
-    pdl_wait();  // (its predecessor is the zero-fill of the gradient records; this lets preprocess_bwd_kernel be scheduled early)
 
     const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;

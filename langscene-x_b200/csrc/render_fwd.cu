@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(32, (CT4 == 24 || CT4 == 28) ? 32 : 0) render_
     using Stage = ListStage<RS>;
     constexpr int CHUNK = Stage::CHUNK;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    pdl_wait();
 
     const int tile = blockIdx.x >> 3, warp = blockIdx.x & 7;
     const int tile_x = tile % p.grid_x, tile_y = tile / p.grid_x;
@@ -182,7 +181,7 @@ int launch_fwd_t(const RenderParams& p, cudaStream_t stream, bool debug) {
     constexpr int RS = (REC_HEAD + CT4 + 7) & ~7;
     const size_t smem = ListStage<RS>::kSmemBytes;  // two 16-record buffers: ~5 KB, so 32 blocks fit on an SM
     const long long blocks = (long long)p.grid_x * p.grid_y * 8;
-    launch_pdl(render_fwd_kernel<CT4>, blocks, 32, smem, stream, p);
+    render_fwd_kernel<CT4><<<(unsigned)blocks, 32, smem, stream>>>(p);
     LSX_KERNEL_OK(stream, debug);
     return 0;
 }
